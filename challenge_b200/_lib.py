@@ -1,0 +1,99 @@
+"""ctypes binding of libiris.so (include/iris.h).  There is NO CPU fallback: if the
+shared library is missing or no CUDA device is present, importing the compute entry
+points fails loudly."""
+import ctypes as C
+import os
+
+from .errors import InvalidArgumentError, IrisError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libiris.so')
+
+IRIS_OK, IRIS_ERR_INVALID, IRIS_ERR_CUDA, IRIS_ERR_EMPTY_RANGE, IRIS_ERR_STATE, \
+    IRIS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+BANK_BG, BANK_VOICE, BANK_NOISE = 0, 1, 2
+FEAT_COMPLEX, FEAT_MAGPHASE, FEAT_LOG_MAGPHASE, FEAT_MEL, FEAT_LOGMEL, FEAT_LOGMEL_MINMAX = range(6)
+REMAP_NONE, REMAP_STEREO_MONO, REMAP_MERGE_AUG = 0, 1, 2
+
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+
+
+class IrisPlan(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('n_frame', C.c_int32), ('max_voices', C.c_int32),
+        ('max_noises', C.c_int32), ('min_ratio', C.c_float), ('min_noise_ratio', C.c_float),
+        ('bg_id', _i32p), ('bg_offset', _i32p), ('n_voices', _i32p), ('voice_id', _i32p),
+        ('voice_gain', _f32p), ('voice_offset', _i32p), ('n_noises', _i32p), ('noise_id', _i32p),
+        ('noise_gain', _f32p), ('noise_offset', _i32p), ('n_time_masks', C.c_int32),
+        ('n_freq_masks', C.c_int32), ('time_masks', _i32p), ('freq_masks', _i32p),
+        ('stft_filter', C.c_int32), ('chan_remap', C.c_int32), ('n_out_chan', C.c_int32),
+        ('merge_factor', _f32p),
+    ]
+
+
+# name -> (restype, argtypes); also the list of symbols include/iris.h declares
+SIGNATURES = {
+    'iris_abi_version': (C.c_int, []),
+    'iris_last_error': (C.c_char_p, []),
+    'iris_ctx_create': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    'iris_ctx_destroy': (C.c_int, [C.c_void_p]),
+    'iris_set_mel': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'iris_bank_register': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'iris_bank_info': (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, C.c_void_p]),
+    'iris_bank_activity': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'iris_plan_upload': (C.c_int, [C.c_void_p, C.POINTER(IrisPlan), C.c_void_p]),
+    'iris_labels': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'iris_features': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'iris_stft': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                            C.c_void_p]),
+    'iris_metric_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    'iris_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
+    'iris_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i32p, C.c_int]),
+    'iris_plan_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libiris.so (built in-tree by ``python -m challenge_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'challenge_b200/libiris.so is missing -- build it with '
+            '`python -m challenge_b200.build` (needs nvcc).  There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in list(SIGNATURES.items()) + list(_ops_signatures().items()):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ops_signatures():
+    try:
+        from ._ops_sig import OPS_SIGNATURES
+        return OPS_SIGNATURES
+    except ImportError:
+        return {}
+
+
+def check(rc):
+    if rc == IRIS_OK:
+        return
+    msg = load().iris_last_error().decode('utf-8', 'replace')
+    if rc == IRIS_ERR_EMPTY_RANGE:
+        raise InvalidArgumentError(msg)
+    if rc == IRIS_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == IRIS_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise IrisError('libiris error %d: %s' % (rc, msg))

@@ -1,0 +1,773 @@
+// extern "C" surface of libiris (include/iris.h): context, bank registration, batch plan,
+// and the launches of the hot-path kernels.  Host-side logic only; kernels live in k_*.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/iris.h"
+#include "iris_common.cuh"
+#include "iris_launch.h"
+
+using namespace iris;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return IRIS_ERR_CUDA;
+}
+#define CU(x)                                         \
+    do {                                              \
+        cudaError_t e_ = (x);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct Bank {
+    bool ready = false;
+    int n_items = 0, n_chan = 0, n_classes = 0;
+    std::vector<int64_t> offsets;      // samples per channel, cumulative
+    std::vector<int64_t> pad_offsets;  // padded floats per channel, cumulative
+    std::vector<int32_t> n_frames;
+    int max_frames = 0;
+    DevBuf padded, activity, labels, d_n_frames;
+    std::vector<uint8_t> h_activity;   // host mirror (voice bank)
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct iris_ctx {
+    int device = 0;
+    int num_sms = 148;
+    Bank banks[3];
+    DevBuf tw, whalf;
+    // mel (CSR by mel bin)
+    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0;
+    DevBuf mel_ptr, mel_f, mel_w;
+    // plan
+    bool has_plan = false, labels_done = false;
+    int B = 0, T = 0, V = 0, M = 0, C = 0;
+    int n_tmask = 0, n_fmask = 0, filter_k = 0, remap = 0, c_out = 0;
+    std::vector<Seg> h_segs;
+    std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
+    std::vector<int32_t> h_seg_ptr;
+    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;
+    void* h_stage = nullptr;  // pinned staging for the plan blob
+    size_t h_stage_cap = 0;
+    cudaEvent_t stage_free = nullptr;
+    // device views into plan_blob
+    Seg* d_segs = nullptr;
+    int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
+            *d_voice_shift = nullptr, *d_tmask = nullptr, *d_fmask = nullptr;
+    float *d_merge_f = nullptr, *d_merge_sf = nullptr;
+    // roofline measurement hook
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+};
+
+namespace {
+
+int set_device(iris_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return IRIS_OK;
+}
+
+int build_tables(iris_ctx* c) {
+    std::vector<float> tw(2 * 512), wh(512);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const double a = -2.0 * M_PI * double(k1 * n2) / 512.0;
+            tw[2 * (k1 * 16 + n2)] = float(cos(a));
+            tw[2 * (k1 * 16 + n2) + 1] = float(sin(a));
+        }
+    // periodic Hann (torch.hann_window(512)), pre-scaled by the 1/2 of the two-channel split
+    for (int n = 0; n < 512; ++n) wh[n] = float(0.5 * (0.5 - 0.5 * cos(2.0 * M_PI * n / 512.0)));
+    CU(c->tw.reserve(tw.size() * 4));
+    CU(c->whalf.reserve(wh.size() * 4));
+    CU(cudaMemcpy(c->tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->whalf.p, wh.data(), wh.size() * 4, cudaMemcpyHostToDevice));
+    return IRIS_OK;
+}
+
+void fill_common(iris_ctx* c, FusedParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.tw = c->tw.as<float2>();
+    p.whalf = c->whalf.as<float>();
+    p.n_mel = c->n_mel;
+    p.mel_f_lo = c->mel_f_lo;
+    p.mel_f_n = c->mel_f_n;
+    p.mel_ptr = c->mel_ptr.as<int32_t>();
+    p.mel_f = c->mel_f.as<int16_t>();
+    p.mel_w = c->mel_w.as<float>();
+}
+
+int ensure_stage(iris_ctx* c, size_t bytes) {
+    if (bytes <= c->h_stage_cap) return IRIS_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU(cudaMallocHost(&c->h_stage, want));
+    c->h_stage_cap = want;
+    return IRIS_OK;
+}
+
+int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, cudaStream_t st) {
+    const Bank& vb = c->banks[IRIS_BANK_VOICE];
+    const int K = vb.ready ? vb.n_classes : 0;
+    if (c->V > 0 && !vb.ready) return fail(IRIS_ERR_STATE, "voice bank not registered");
+    CU(c->keep.reserve(size_t(c->B) * (c->V > 0 ? c->V : 1)));
+    if (c->V == 0 || K == 0) {
+        c->labels_done = true;
+        return IRIS_OK;
+    }
+    float* frame = d_frame;
+    if (!frame) {
+        CU(c->scratch_labels.reserve(size_t(c->B) * c->T * K * 4));
+        frame = c->scratch_labels.as<float>();
+    }
+    LabelParams lp;
+    lp.B = c->B; lp.T = c->T; lp.V = c->V; lp.K = K;
+    lp.n_voices = c->d_n_voices;
+    lp.voice_id = c->d_voice_id;
+    lp.voice_shift = c->d_voice_shift;
+    lp.n_frames = vb.d_n_frames.as<int32_t>();
+    lp.activity = vb.activity.as<uint8_t>();
+    lp.act_stride = vb.max_frames;
+    lp.bank_labels = vb.labels.as<float>();
+    lp.labels_vtk = d_vtk;
+    lp.frame_labels = frame;
+    lp.keep = c->keep.as<uint8_t>();
+    CU(launch_labels(lp, st));
+    if (d_keep_out)
+        CU(cudaMemcpyAsync(d_keep_out, c->keep.p, size_t(c->B) * c->V, cudaMemcpyDeviceToDevice, st));
+    c->labels_done = true;
+    return IRIS_OK;
+}
+
+int timed_fused(iris_ctx* c, const FusedParams& p, int mode, cudaStream_t st) {
+    if (!c->profile) {
+        CU(launch_fused(p, mode, c->num_sms, st));
+        return IRIS_OK;
+    }
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        c->prof_events.emplace_back(a, b);
+    }
+    auto& ev = c->prof_events[c->prof_used++];
+    CU(cudaEventRecord(ev.first, st));
+    CU(launch_fused(p, mode, c->num_sms, st));
+    CU(cudaEventRecord(ev.second, st));
+    return IRIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int iris_abi_version(void) { return IRIS_ABI_VERSION; }
+const char* iris_last_error(void) { return g_err.c_str(); }
+
+int iris_ctx_create(int device, iris_ctx** out) {
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(IRIS_ERR_CUDA, std::string("no CUDA device (libiris has no CPU fallback): ") +
+                                       cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(IRIS_ERR_INVALID, "device index out of range");
+    iris_ctx* c = new iris_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaSetDevice");
+    }
+    if (prop.major != 10) {
+        delete c;
+        return fail(IRIS_ERR_UNSUPPORTED, "libiris is built for sm_100a (Blackwell B200) only");
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if ((e = cudaEventCreateWithFlags(&c->stage_free, cudaEventDisableTiming)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaEventCreate");
+    }
+    int rc = build_tables(c);
+    if (rc != IRIS_OK) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return IRIS_OK;
+}
+
+int iris_ctx_destroy(iris_ctx* c) {
+    if (!c) return IRIS_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& b : c->banks) {
+        b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
+    }
+    for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_ptr, &c->mel_f, &c->mel_w, &c->plan_blob, &c->keep,
+                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small})
+        d->release();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->stage_free) cudaEventDestroy(c->stage_free);
+    for (auto& ev : c->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    delete c;
+    return IRIS_OK;
+}
+
+int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
+    if (!c || !w) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (n_bins != kBins) return fail(IRIS_ERR_INVALID, "n_bins must be 257 (n_fft 512)");
+    if (n_mel < 1 || n_mel > 256) return fail(IRIS_ERR_INVALID, "n_mel must be in [1, 256]");
+    int rc = set_device(c);
+    if (rc) return rc;
+    std::vector<int32_t> ptr(n_mel + 1, 0);
+    std::vector<int16_t> fi;
+    std::vector<float> fw;
+    int f_lo = kBins, f_hi = -1;
+    for (int m = 0; m < n_mel; ++m) {
+        for (int f = 0; f < n_bins; ++f) {
+            const float v = w[size_t(f) * n_mel + m];
+            if (v != 0.f) {
+                fi.push_back(int16_t(f));
+                fw.push_back(v);
+                if (f < f_lo) f_lo = f;
+                if (f > f_hi) f_hi = f;
+            }
+        }
+        ptr[m + 1] = int32_t(fi.size());
+    }
+    if (f_hi < 0) { f_lo = 0; f_hi = 0; }
+    if (f_hi - f_lo + 1 > fused_max_mel_window())
+        return fail(IRIS_ERR_UNSUPPORTED,
+                    "mel matrix support spans more than 136 bins; use the unfused mel projection");
+    CU(c->mel_ptr.reserve(ptr.size() * 4));
+    CU(c->mel_f.reserve(fi.size() * 2 + 2));
+    CU(c->mel_w.reserve(fw.size() * 4 + 4));
+    CU(cudaMemcpy(c->mel_ptr.p, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    if (!fi.empty()) {
+        CU(cudaMemcpy(c->mel_f.p, fi.data(), fi.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
+    }
+    c->n_mel = n_mel;
+    c->mel_f_lo = f_lo;
+    c->mel_f_n = f_hi - f_lo + 1;
+    return IRIS_OK;
+}
+
+int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const float* wav,
+                       const int64_t* offsets, const float* labels, int n_classes, int normalize,
+                       iris_stream stream) {
+    if (!c || !wav || !offsets) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(IRIS_ERR_INVALID, "bad bank kind");
+    if (n_items < 1 || n_chan < 1) return fail(IRIS_ERR_INVALID, "empty bank");
+    if (kind == IRIS_BANK_VOICE && (!labels || n_classes < 1))
+        return fail(IRIS_ERR_INVALID, "voice bank needs labels [n_items, n_classes]");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Bank& b = c->banks[kind];
+    b.ready = false;
+    b.n_items = n_items;
+    b.n_chan = n_chan;
+    b.n_classes = n_classes;
+    b.offsets.assign(offsets, offsets + n_items + 1);
+    b.pad_offsets.assign(n_items + 1, 0);
+    b.n_frames.assign(n_items, 0);
+    b.max_frames = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int64_t n = offsets[i + 1] - offsets[i];
+        if (n <= kNFft / 2)
+            return fail(IRIS_ERR_INVALID,
+                        "source shorter than 257 samples (reflect padding needs pad < length)");
+        const int64_t kT = 1 + n / kHop;
+        b.n_frames[i] = int32_t(kT);
+        if (kT > b.max_frames) b.max_frames = int(kT);
+        b.pad_offsets[i + 1] = b.pad_offsets[i] + 256 * (kT + 1);
+    }
+    for (int k = 0; k < 3; ++k)
+        if (k != kind && c->banks[k].ready && c->banks[k].n_chan != n_chan)
+            return fail(IRIS_ERR_INVALID, "all banks must have the same channel count");
+    const size_t wav_floats = size_t(offsets[n_items]) * n_chan;
+    const size_t pad_floats = size_t(b.pad_offsets[n_items]) * n_chan;
+    DevBuf raw, d_off;
+    CU(raw.reserve(wav_floats * 4));
+    CU(d_off.reserve(size_t(n_items + 1) * 16));
+    CU(b.padded.reserve(pad_floats * 4));
+    CU(b.d_n_frames.reserve(size_t(n_items) * 4));
+    CU(cudaMemcpyAsync(raw.p, wav + size_t(offsets[0]) * n_chan, wav_floats * 4, cudaMemcpyDefault, st));
+    std::vector<int64_t> rel(n_items + 1);
+    for (int i = 0; i <= n_items; ++i) rel[i] = offsets[i] - offsets[0];
+    int64_t* d_o = d_off.as<int64_t>();
+    CU(cudaMemcpyAsync(d_o, rel.data(), size_t(n_items + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_o + n_items + 1, b.pad_offsets.data(), size_t(n_items + 1) * 8,
+                       cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b.d_n_frames.p, b.n_frames.data(), size_t(n_items) * 4,
+                       cudaMemcpyHostToDevice, st));
+    CU(launch_bank_prepare(raw.as<float>(), d_o, d_o + n_items + 1, n_items, n_chan, normalize,
+                           b.padded.as<float>(), st));
+    if (kind == IRIS_BANK_VOICE) {
+        CU(b.labels.reserve(size_t(n_items) * n_classes * 4));
+        CU(cudaMemcpyAsync(b.labels.p, labels, size_t(n_items) * n_classes * 4,
+                           cudaMemcpyHostToDevice, st));
+        // activity: one STFT pass over every voice, frame active iff any coefficient > 0
+        const size_t act_bytes = size_t(n_items) * b.max_frames;
+        CU(b.activity.reserve(act_bytes));
+        CU(cudaMemsetAsync(b.activity.p, 0, act_bytes, st));
+        std::vector<Seg> segs(n_items);
+        std::vector<int32_t> ptr(n_items + 1);
+        for (int i = 0; i < n_items; ++i) {
+            Seg& s = segs[i];
+            const int64_t plen = 256 * (int64_t(b.n_frames[i]) + 1);
+            s.base = b.padded.as<float>() + size_t(b.pad_offsets[i]) * n_chan;
+            s.chan_stride = int32_t(plen);
+            s.n_rows = b.n_frames[i] + 1;
+            s.shift = 0;
+            s.t_lo = 0;
+            s.t_hi = b.n_frames[i];
+            s.gain = 1.f;
+            s.keep_idx = -1;
+            s.pad_ = 0;
+            ptr[i] = i;
+        }
+        ptr[n_items] = n_items;
+        DevBuf d_segs;
+        CU(d_segs.reserve(segs.size() * sizeof(Seg) + ptr.size() * 4));
+        Seg* ds = d_segs.as<Seg>();
+        int32_t* dp = reinterpret_cast<int32_t*>(ds + n_items);
+        CU(cudaMemcpyAsync(ds, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dp, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice, st));
+        FusedParams p;
+        fill_common(c, p);
+        p.segs = ds;
+        p.seg_ptr = dp;
+        p.B = n_items;
+        p.T = b.max_frames;
+        p.C = n_chan;
+        p.n_pairs = (n_chan + 1) / 2;
+        p.c_out = n_chan;
+        p.activity = b.activity.as<uint8_t>();
+        CU(launch_fused(p, FM_ACTIVITY, c->num_sms, st));
+        b.h_activity.resize(act_bytes);
+        CU(cudaMemcpyAsync(b.h_activity.data(), b.activity.p, act_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        d_segs.release();
+    }
+    CU(cudaStreamSynchronize(st));
+    raw.release();
+    d_off.release();
+    b.ready = true;
+    c->has_plan = false;
+    return IRIS_OK;
+}
+
+int iris_bank_info(iris_ctx* c, int kind, int32_t* n_items, int32_t* n_chan, int32_t* n_frames) {
+    if (!c || kind < 0 || kind > 2) return fail(IRIS_ERR_INVALID, "bad argument");
+    const Bank& b = c->banks[kind];
+    if (!b.ready) return fail(IRIS_ERR_STATE, "bank not registered");
+    if (n_items) *n_items = b.n_items;
+    if (n_chan) *n_chan = b.n_chan;
+    if (n_frames) memcpy(n_frames, b.n_frames.data(), size_t(b.n_items) * 4);
+    return IRIS_OK;
+}
+
+int iris_bank_activity(iris_ctx* c, int item, uint8_t* host_out) {
+    if (!c || !host_out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    const Bank& b = c->banks[IRIS_BANK_VOICE];
+    if (!b.ready) return fail(IRIS_ERR_STATE, "voice bank not registered");
+    if (item < 0 || item >= b.n_items) return fail(IRIS_ERR_INVALID, "item out of range");
+    memcpy(host_out, b.h_activity.data() + size_t(item) * b.max_frames, size_t(b.n_frames[item]));
+    return IRIS_OK;
+}
+
+int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
+    if (!c || !pl) return fail(IRIS_ERR_INVALID, "NULL argument");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = pl->batch, T = pl->n_frame, V = pl->max_voices, M = pl->max_noises;
+    if (B < 1 || T < 1 || V < 0 || M < 0) return fail(IRIS_ERR_INVALID, "bad plan sizes");
+    const Bank& bg = c->banks[IRIS_BANK_BG];
+    const Bank& vb = c->banks[IRIS_BANK_VOICE];
+    const Bank& nb = c->banks[IRIS_BANK_NOISE];
+    if (!bg.ready) return fail(IRIS_ERR_STATE, "background bank not registered");
+    if (V > 0 && !vb.ready) return fail(IRIS_ERR_STATE, "voice bank not registered");
+    if (M > 0 && !nb.ready) return fail(IRIS_ERR_STATE, "noise bank not registered");
+    if (!pl->bg_id || !pl->bg_offset) return fail(IRIS_ERR_INVALID, "bg_id / bg_offset NULL");
+    if (V > 0 && (!pl->n_voices || !pl->voice_id || !pl->voice_gain || !pl->voice_offset))
+        return fail(IRIS_ERR_INVALID, "voice draws NULL");
+    if (M > 0 && (!pl->n_noises || !pl->noise_id || !pl->noise_gain || !pl->noise_offset))
+        return fail(IRIS_ERR_INVALID, "noise draws NULL");
+    const int C = bg.n_chan;
+    const int n_tm = pl->time_masks ? pl->n_time_masks : 0;
+    const int n_fm = pl->freq_masks ? pl->n_freq_masks : 0;
+    if (n_tm < 0 || n_tm > 64) return fail(IRIS_ERR_UNSUPPORTED, "more than 64 time masks");
+    if (n_fm < 0 || n_fm > 4) return fail(IRIS_ERR_UNSUPPORTED, "more than 4 frequency masks");
+    int c_out = C;
+    if (pl->chan_remap != IRIS_REMAP_NONE) {
+        // data_utils.py:104 -- ValueError('This augment can be used in 2 channel audio')
+        if (C != 2) return fail(IRIS_ERR_INVALID, "channel remap needs 2-channel audio");
+        c_out = pl->chan_remap == IRIS_REMAP_STEREO_MONO ? 3 : pl->n_out_chan;
+        if (c_out < 3 || c_out > 16) return fail(IRIS_ERR_INVALID, "bad n_out_chan");
+        if (pl->chan_remap == IRIS_REMAP_MERGE_AUG && !pl->merge_factor)
+            return fail(IRIS_ERR_INVALID, "merge_factor NULL");
+    }
+
+    c->h_segs.clear();
+    c->h_seg_len.clear();
+    c->h_seg_ptr.assign(B + 1, 0);
+    std::vector<int32_t> vshift(size_t(B) * (V > 0 ? V : 1), 0);
+    auto push = [&](const Bank& bank, int id, int shift, int lo, int hi, float gain, int keep_idx) {
+        if (lo >= hi) return;
+        Seg s;
+        const int64_t plen = 256 * (int64_t(bank.n_frames[id]) + 1);
+        s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * bank.n_chan;
+        s.chan_stride = int32_t(plen);
+        s.n_rows = bank.n_frames[id] + 1;
+        s.shift = shift;
+        s.t_lo = lo;
+        s.t_hi = hi;
+        s.gain = gain;
+        s.keep_idx = keep_idx;
+        s.pad_ = 0;
+        c->h_segs.push_back(s);
+        c->h_seg_len.push_back(bank.offsets[id + 1] - bank.offsets[id]);
+    };
+    char msg[160];
+    for (int b = 0; b < B; ++b) {
+        // background: tile ceil(T/bgT) times, crop at bg_offset (pipeline.py:29-35)
+        const int id = pl->bg_id[b];
+        if (id < 0 || id >= bg.n_items) return fail(IRIS_ERR_INVALID, "bg_id out of range");
+        const int bgT = bg.n_frames[id];
+        const int reps = (T + bgT - 1) / bgT;
+        const int ob = pl->bg_offset[b];
+        if (ob < 0 || ob > bgT * reps - T) {
+            snprintf(msg, sizeof msg, "clip %d: bg_offset %d outside [0, %d]", b, ob, bgT * reps - T);
+            return fail(IRIS_ERR_INVALID, msg);
+        }
+        for (int r = 0; r <= reps; ++r) {
+            const int lo = std::max(0, r * bgT - ob), hi = std::min(T, (r + 1) * bgT - ob);
+            push(bg, id, ob - r * bgT, lo, hi, 1.f, -1);
+        }
+        // voices (pipeline.py:41-84)
+        if (V > 0) {
+            int nv = pl->n_voices[b];
+            if (V == 1) nv = 1;
+            if (nv < 0 || (V > 1 && nv >= V)) {
+                snprintf(msg, sizeof msg, "clip %d: n_voices %d outside [1, %d)", b, nv, V);
+                return fail(IRIS_ERR_INVALID, msg);
+            }
+            int vP = 0;   // padded_batch: the group's longest member (pipeline.py:155-156)
+            for (int v = 0; v < V; ++v) {
+                const int vid = pl->voice_id[size_t(b) * V + v];
+                if (vid < 0 || vid >= vb.n_items) return fail(IRIS_ERR_INVALID, "voice_id out of range");
+                vP = std::max(vP, int(vb.n_frames[vid]));
+            }
+            for (int v = 0; v < nv; ++v) {
+                const int vid = pl->voice_id[size_t(b) * V + v];
+                // pad_size = n_frame - int32(min_ratio * float32(v_frame))   (pipeline.py:58-59)
+                const int pad = T - int(int32_t(float(pl->min_ratio) * float(vP)));
+                const int len = pad > 0 ? vP + 2 * pad : vP;
+                const int s0 = pad > 0 ? pad : 0;
+                const int maxval = len - T;
+                if (maxval <= 0) {
+                    snprintf(msg, sizeof msg,
+                             "clip %d voice %d: empty offset range [0, %d) (pipeline.py:68-69 raises)",
+                             b, v, maxval);
+                    return fail(IRIS_ERR_EMPTY_RANGE, msg);
+                }
+                const int off = pl->voice_offset[size_t(b) * V + v];
+                if (off < 0 || off >= maxval) {
+                    snprintf(msg, sizeof msg, "clip %d voice %d: offset %d outside [0, %d)", b, v, off, maxval);
+                    return fail(IRIS_ERR_INVALID, msg);
+                }
+                const int shift = off - s0;
+                vshift[size_t(b) * V + v] = shift;
+                const int kT = vb.n_frames[vid];
+                push(vb, vid, shift, std::max(0, -shift), std::min(T, kT - shift),
+                     pl->voice_gain[size_t(b) * V + v], b * V + v);
+            }
+        }
+        // noises (pipeline.py:86-106)
+        if (M > 0) {
+            const int nn = pl->n_noises[b];
+            if (nn < 0 || nn >= M) {
+                snprintf(msg, sizeof msg, "clip %d: n_noises %d outside [0, %d)", b, nn, M);
+                return fail(IRIS_ERR_INVALID, msg);
+            }
+            int nP = 0;
+            for (int n = 0; n < M; ++n) {
+                const int nid = pl->noise_id[size_t(b) * M + n];
+                if (nid < 0 || nid >= nb.n_items) return fail(IRIS_ERR_INVALID, "noise_id out of range");
+                nP = std::max(nP, int(nb.n_frames[nid]));
+            }
+            for (int n = 0; n < nn; ++n) {
+                const int nid = pl->noise_id[size_t(b) * M + n];
+                const int pad = T - int(int32_t(float(pl->min_noise_ratio) * float(nP)));
+                const int len = pad > 0 ? nP + 2 * pad : nP;
+                const int s0 = pad > 0 ? pad : 0;
+                const int off = pl->noise_offset[size_t(b) * M + n];
+                if (len < T || off < 0 || off > len - T) {
+                    snprintf(msg, sizeof msg, "clip %d noise %d: offset %d outside [0, %d]", b, n, off, len - T);
+                    return fail(IRIS_ERR_INVALID, msg);
+                }
+                const int shift = off - s0;
+                const int kT = nb.n_frames[nid];
+                push(nb, nid, shift, std::max(0, -shift), std::min(T, kT - shift),
+                     pl->noise_gain[size_t(b) * M + n], -1);
+            }
+        }
+        c->h_seg_ptr[b + 1] = int32_t(c->h_segs.size());
+        // mask draws (transforms.py:25-26)
+        for (int i = 0; i < n_tm; ++i) {
+            const int size = pl->time_masks[(size_t(b) * n_tm + i) * 2];
+            const int off = pl->time_masks[(size_t(b) * n_tm + i) * 2 + 1];
+            if (size < 0 || off < 0 || off + size > T) return fail(IRIS_ERR_INVALID, "time mask outside the clip");
+        }
+        for (int i = 0; i < n_fm; ++i) {
+            const int size = pl->freq_masks[(size_t(b) * n_fm + i) * 2];
+            const int off = pl->freq_masks[(size_t(b) * n_fm + i) * 2 + 1];
+            if (size < 0 || off < 0 || off + size > kBins) return fail(IRIS_ERR_INVALID, "freq mask outside the spectrum");
+        }
+    }
+
+    // ---- pack everything into one pinned blob, one H2D copy ----
+    const int n_extra = (pl->chan_remap == IRIS_REMAP_MERGE_AUG) ? c_out - 2 : 0;
+    size_t o = 0;
+    const size_t o_segs = o; o = align_up(o + c->h_segs.size() * sizeof(Seg), 16);
+    const size_t o_ptr = o;  o = align_up(o + size_t(B + 1) * 4, 16);
+    const size_t o_nv = o;   o = align_up(o + size_t(B) * 4, 16);
+    const size_t o_vid = o;  o = align_up(o + size_t(B) * std::max(V, 1) * 4, 16);
+    const size_t o_vsh = o;  o = align_up(o + size_t(B) * std::max(V, 1) * 4, 16);
+    const size_t o_tm = o;   o = align_up(o + size_t(B) * n_tm * 8, 16);
+    const size_t o_fm = o;   o = align_up(o + size_t(B) * n_fm * 8, 16);
+    const size_t o_mf = o;   o = align_up(o + size_t(B) * n_extra * 4, 16);
+    const size_t o_msf = o;  o = align_up(o + size_t(B) * n_extra * 4, 16);
+    const size_t total = o;
+    if (c->h_stage) CU(cudaEventSynchronize(c->stage_free));   // previous upload done with it
+    rc = ensure_stage(c, total);
+    if (rc) return rc;
+    CU(c->plan_blob.reserve(total));
+    char* h = static_cast<char*>(c->h_stage);
+    memcpy(h + o_segs, c->h_segs.data(), c->h_segs.size() * sizeof(Seg));
+    memcpy(h + o_ptr, c->h_seg_ptr.data(), size_t(B + 1) * 4);
+    if (V > 0) {
+        int32_t* nv = reinterpret_cast<int32_t*>(h + o_nv);
+        for (int b = 0; b < B; ++b) nv[b] = (V == 1) ? 1 : pl->n_voices[b];
+        memcpy(h + o_vid, pl->voice_id, size_t(B) * V * 4);
+        memcpy(h + o_vsh, vshift.data(), size_t(B) * V * 4);
+    }
+    if (n_tm) memcpy(h + o_tm, pl->time_masks, size_t(B) * n_tm * 8);
+    if (n_fm) memcpy(h + o_fm, pl->freq_masks, size_t(B) * n_fm * 8);
+    if (n_extra) {
+        memcpy(h + o_mf, pl->merge_factor, size_t(B) * n_extra * 4);
+        float* sf = reinterpret_cast<float*>(h + o_msf);
+        for (size_t i = 0; i < size_t(B) * n_extra; ++i) sf[i] = sqrtf(1.f - pl->merge_factor[i]);
+    }
+    CU(cudaMemcpyAsync(c->plan_blob.p, h, total, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->stage_free, st));
+    char* d = c->plan_blob.as<char>();
+    c->d_segs = reinterpret_cast<Seg*>(d + o_segs);
+    c->d_seg_ptr = reinterpret_cast<int32_t*>(d + o_ptr);
+    c->d_n_voices = reinterpret_cast<int32_t*>(d + o_nv);
+    c->d_voice_id = reinterpret_cast<int32_t*>(d + o_vid);
+    c->d_voice_shift = reinterpret_cast<int32_t*>(d + o_vsh);
+    c->d_tmask = n_tm ? reinterpret_cast<int32_t*>(d + o_tm) : nullptr;
+    c->d_fmask = n_fm ? reinterpret_cast<int32_t*>(d + o_fm) : nullptr;
+    c->d_merge_f = n_extra ? reinterpret_cast<float*>(d + o_mf) : nullptr;
+    c->d_merge_sf = n_extra ? reinterpret_cast<float*>(d + o_msf) : nullptr;
+    c->B = B; c->T = T; c->V = V; c->M = M; c->C = C;
+    c->n_tmask = n_tm; c->n_fmask = n_fm;
+    c->filter_k = pl->stft_filter > 0 ? pl->stft_filter : 0;
+    c->remap = pl->chan_remap;
+    c->c_out = c_out;
+    c->has_plan = true;
+    c->labels_done = false;
+    return IRIS_OK;
+}
+
+int iris_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep, iris_stream stream) {
+    if (!c) return fail(IRIS_ERR_INVALID, "NULL ctx");
+    if (!c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
+    int rc = set_device(c);
+    if (rc) return rc;
+    return run_labels(c, d_vtk, d_frame, d_keep, static_cast<cudaStream_t>(stream));
+}
+
+int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
+    if (!c || !d_out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
+    if (mode < IRIS_FEAT_COMPLEX || mode > IRIS_FEAT_LOGMEL_MINMAX)
+        return fail(IRIS_ERR_INVALID, "bad feature mode");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!c->labels_done) {   // accept flags of the voices are an input of the mix
+        rc = run_labels(c, nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+    }
+    const bool mel = mode >= IRIS_FEAT_MEL;
+    if (mel && c->n_mel == 0) return fail(IRIS_ERR_STATE, "iris_set_mel not called");
+    if (mel && c->remap != IRIS_REMAP_NONE)
+        return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
+    FusedParams p;
+    fill_common(c, p);
+    p.segs = c->d_segs;
+    p.seg_ptr = c->d_seg_ptr;
+    p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
+    p.B = c->B; p.T = c->T; p.C = c->C;
+    p.n_pairs = (c->C + 1) / 2;
+    p.c_out = c->c_out;
+    p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
+    p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
+    p.filter_k = c->filter_k;
+    p.remap = c->remap;
+    p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
+    p.out = d_out;
+    if (mel) {
+        if (mode == IRIS_FEAT_LOGMEL_MINMAX) {
+            CU(c->minmax.reserve(size_t(c->B) * 8));
+            CU(cudaMemsetAsync(c->minmax.p, 0, size_t(c->B) * 8, st));
+            p.minmax = c->minmax.as<uint32_t>();
+        }
+        rc = timed_fused(c, p, FM_MEL, st);
+        if (rc) return rc;
+        CU(launch_logmel_post(d_out, p.minmax, c->B, size_t(c->n_mel) * c->T * c->C,
+                              mode == IRIS_FEAT_LOGMEL_MINMAX, mode != IRIS_FEAT_MEL, st));
+    } else {
+        rc = timed_fused(c, p, mode, st);
+        if (rc) return rc;
+    }
+    return IRIS_OK;
+}
+
+int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normalize, float* d_out,
+              iris_stream stream) {
+    if (!c || !wav || !d_out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (n_chan < 1 || n <= kNFft / 2) return fail(IRIS_ERR_INVALID, "need n_samples > 256");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t kT = 1 + n / kHop, plen = 256 * (kT + 1);
+    CU(c->stft_pad.reserve(size_t(plen + n) * n_chan * 4));
+    CU(c->stft_small.reserve(256));
+    float* P = c->stft_pad.as<float>();
+    float* raw = P + size_t(plen) * n_chan;
+    CU(cudaMemcpyAsync(raw, wav, size_t(n) * n_chan * 4, cudaMemcpyDefault, st));
+    struct Small { int64_t off[2]; int64_t poff[2]; Seg seg; int32_t ptr[2]; } h;
+    h.off[0] = 0; h.off[1] = n; h.poff[0] = 0; h.poff[1] = plen;
+    h.seg.base = P; h.seg.chan_stride = int32_t(plen); h.seg.n_rows = int32_t(kT + 1);
+    h.seg.shift = 0; h.seg.t_lo = 0; h.seg.t_hi = int32_t(kT); h.seg.gain = 1.f;
+    h.seg.keep_idx = -1; h.seg.pad_ = 0;
+    h.ptr[0] = 0; h.ptr[1] = 1;
+    CU(cudaMemcpyAsync(c->stft_small.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // h is on the stack
+    Small* d = c->stft_small.as<Small>();
+    CU(launch_bank_prepare(raw, d->off, d->poff, 1, n_chan, normalize, P, st));
+    FusedParams p;
+    fill_common(c, p);
+    p.segs = &d->seg;
+    p.seg_ptr = d->ptr;
+    p.B = 1; p.T = int32_t(kT); p.C = n_chan;
+    p.n_pairs = (n_chan + 1) / 2;
+    p.c_out = n_chan;
+    p.out = d_out;
+    CU(launch_fused(p, FM_COMPLEX, c->num_sms, st));
+    return IRIS_OK;
+}
+
+int iris_metric_counts(iris_ctx* c, const float* y_true, const float* y_pred, int B, int T, int K,
+                       float thr, int32_t* d_triples, uint64_t* d_tpfpfn, float* d_er,
+                       iris_stream stream) {
+    if (!c || !y_true || !y_pred || !d_triples) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (B < 1 || T < 1 || K < 1) return fail(IRIS_ERR_INVALID, "bad shape");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(launch_metric_counts(y_true, y_pred, B, T, K, thr, d_triples,
+                            reinterpret_cast<unsigned long long*>(d_tpfpfn), st));
+    if (d_er) CU(launch_er_finalize(d_triples, B, d_er, st));
+    return IRIS_OK;
+}
+
+int iris_profile_enable(iris_ctx* c, int enable) {
+    if (!c) return fail(IRIS_ERR_INVALID, "NULL ctx");
+    c->profile = enable != 0;
+    return IRIS_OK;
+}
+
+int iris_profile_read(iris_ctx* c, double* total_ms, int32_t* n_launches, int reset) {
+    if (!c) return fail(IRIS_ERR_INVALID, "NULL ctx");
+    double tot = 0.0;
+    for (size_t i = 0; i < c->prof_used; ++i) {
+        CU(cudaEventSynchronize(c->prof_events[i].second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->prof_events[i].first, c->prof_events[i].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = int32_t(c->prof_used);
+    if (reset) c->prof_used = 0;
+    return IRIS_OK;
+}
+
+int iris_plan_bytes(iris_ctx* c, int mode, const uint8_t* host_keep, int64_t* bytes_in,
+                    int64_t* bytes_out) {
+    if (!c || !c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
+    int64_t in = 0;
+    for (size_t i = 0; i < c->h_segs.size(); ++i) {
+        const Seg& s = c->h_segs[i];
+        if (s.keep_idx >= 0 && host_keep && !host_keep[s.keep_idx]) continue;
+        // frames [t_lo, t_hi) read the samples of rows t_lo+shift .. t_hi+shift once,
+        // never more than the source holds
+        const int64_t samples = std::min<int64_t>(int64_t(s.t_hi - s.t_lo + 1) * 256, c->h_seg_len[i]);
+        in += samples * 4 * c->C;
+    }
+    int64_t out;
+    if (mode >= IRIS_FEAT_MEL) out = int64_t(c->B) * c->n_mel * c->T * c->C * 4;
+    else out = int64_t(c->B) * kBins * c->T * 2 * c->c_out * 4;
+    if (bytes_in) *bytes_in = in;
+    if (bytes_out) *bytes_out = out;
+    return IRIS_OK;
+}
+
+}  // extern "C"

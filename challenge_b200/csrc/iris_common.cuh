@@ -1,0 +1,117 @@
+// Shared device-side definitions for libiris (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fftcore.cuh"
+
+namespace iris {
+
+constexpr int kNFft = 512;
+constexpr int kHop = 256;
+constexpr int kBins = 257;
+
+// One mixing segment of one output clip: source frames k = t + shift of the padded
+// waveform P (P[c][i] = reflect-padded, normalised x[c][i-256]; row h = P[256h .. 256h+256))
+// contribute gain * frame_k to output frames t in [t_lo, t_hi).
+struct Seg {
+    const float* base;    // channel 0 of P
+    int32_t chan_stride;  // floats between channels of P
+    int32_t n_rows;       // kT + 1 rows of 256 floats per channel
+    int32_t shift;        // k = t + shift
+    int32_t t_lo, t_hi;   // valid output frames
+    float gain;
+    int32_t keep_idx;     // index into keep[] (voice accept flags) or -1
+    int32_t pad_;
+};
+static_assert(sizeof(Seg) == 40, "Seg layout");
+
+enum FusedMode : int {
+    FM_COMPLEX = 0,
+    FM_MAGPHASE = 1,
+    FM_LOGMAGPHASE = 2,
+    FM_MEL = 3,
+    FM_ACTIVITY = 4,
+};
+
+enum ChanRemap : int { REMAP_NONE = 0, REMAP_STEREO_MONO = 1, REMAP_MERGE_AUG = 2 };
+
+struct FusedParams {
+    const Seg* segs;
+    const int32_t* seg_ptr;  // [B+1]
+    const uint8_t* keep;     // voice accept flags, may be null
+    int32_t B, T, C;         // clips, frames per clip, input channels
+    int32_t n_pairs;         // ceil(C/2)
+    int32_t c_out;           // output channels (C unless remapped)
+    // SpecAugment rectangles (size, offset) per clip; null => none
+    const int32_t* tmask;
+    int32_t n_tmask;
+    const int32_t* fmask;
+    int32_t n_fmask;
+    int32_t filter_k;  // stft_filter: zero bins 1..k
+    int32_t remap;
+    const float* merge_f;   // [B, c_out-2] factor
+    const float* merge_sf;  // [B, c_out-2] sqrt(1-factor)
+    // outputs
+    float* out;             // layout depends on mode
+    uint8_t* activity;      // FM_ACTIVITY: [B, T]
+    uint32_t* minmax;       // FM_MEL: [B,2] atomicMax of (~bits, bits); may be null
+    // mel projection (CSR by mel bin, ascending f)
+    int32_t n_mel;
+    int32_t mel_f_lo;       // lowest bin with a non-zero weight
+    int32_t mel_f_n;        // number of bins in [f_lo, f_hi]
+    const int32_t* mel_ptr;  // [n_mel+1]
+    const int16_t* mel_f;    // [nnz]
+    const float* mel_w;      // [nnz]
+    // tables
+    const float2* tw;       // [32][16] W512^(k1*n2)
+    const float* whalf;     // [512] 0.5 * hann
+};
+
+// ---- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace iris

@@ -1,0 +1,253 @@
+"""Per-device engine: owns an ``iris_ctx`` and exposes the C ABI with torch tensors for
+device memory and streams (plumbing only -- every kernel is in libiris.so)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .plan import BatchDraws
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def default_mel_matrix(num_mel_bins=80, num_spectrogram_bins=257, sample_rate=16000,
+                       lower_edge_hertz=125.0, upper_edge_hertz=3800.0):
+    """``tf.signal.linear_to_mel_weight_matrix`` (called at transforms.py:55-56), rebuilt
+    op-for-op in float32 in TF 2.2's order: HTK mel ``1127*ln(1+f/700)``, linspace as
+    ``start + step*i``, triangles in the mel domain, DC row zero."""
+    f32 = np.float32
+
+    def linspace(start, stop, num):
+        start, stop = f32(start), f32(stop)
+        step = f32((stop - start) / f32(num - 1))
+        return (start + step * np.arange(num, dtype=np.float32)).astype(np.float32)
+
+    def h2m(f):
+        return (f32(1127.0) * np.log(f32(1.0) + np.asarray(f, np.float32) / f32(700.0))
+                ).astype(np.float32)
+
+    lin = linspace(0.0, f32(sample_rate) / f32(2.0), num_spectrogram_bins)[1:]
+    spec_mel = h2m(lin)[:, None]
+    edges = linspace(h2m(f32(lower_edge_hertz)), h2m(f32(upper_edge_hertz)), num_mel_bins + 2)
+    lower, center, upper = edges[None, :-2], edges[None, 1:-1], edges[None, 2:]
+    w = np.maximum(f32(0), np.minimum((spec_mel - lower) / (center - lower),
+                                      (upper - spec_mel) / (upper - center)))
+    return np.pad(w.astype(np.float32), [[1, 0], [0, 0]])
+
+
+class Engine:
+    """One engine (= one ``iris_ctx``) per CUDA device."""
+
+    def __init__(self, device=0):
+        torch = _torch()
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.IrisError('no CUDA device visible: libiris has no CPU fallback')
+        self.device = torch.device('cuda', int(device))
+        self._ctx = C.c_void_p()
+        L.check(self.lib.iris_ctx_create(int(device), C.byref(self._ctx)))
+        self.n_mel = 0
+        self.bank_frames = {}
+        self.bank_chan = None
+        self.n_classes = 0
+        self._plan = None
+
+    def close(self):
+        if self._ctx:
+            self.lib.iris_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ----
+    def _stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _empty(self, shape, dtype=None):
+        torch = _torch()
+        return torch.empty(shape, dtype=dtype or torch.float32, device=self.device)
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    # ---- configuration ----
+    def set_mel(self, num_mel_bins=80, num_spectrogram_bins=257, sample_rate=16000,
+                mel_matrix=None, **kwargs):
+        w = mel_matrix if mel_matrix is not None else default_mel_matrix(
+            num_mel_bins, num_spectrogram_bins, sample_rate, **kwargs)
+        w = np.ascontiguousarray(w, np.float32)
+        L.check(self.lib.iris_set_mel(self._ctx, w.shape[1], w.shape[0], w.ctypes.data))
+        self.n_mel = w.shape[1]
+        self.mel_matrix = w
+
+    def register_bank(self, kind, waveforms, labels=None, normalize=True):
+        """``waveforms``: list of float32 ``[C, N_i]`` arrays (the audio load_wav reads,
+        data_utils.py:19).  ``labels``: ``[n_items, K]`` one-hot rows (voice bank)."""
+        waves = [np.ascontiguousarray(w, np.float32) for w in waveforms]
+        n_chan = waves[0].shape[0]
+        assert all(w.ndim == 2 and w.shape[0] == n_chan for w in waves), \
+            'each waveform must be [chan, samples]'
+        offsets = np.zeros(len(waves) + 1, np.int64)
+        offsets[1:] = np.cumsum([w.shape[1] for w in waves])
+        packed = np.concatenate([w.reshape(-1) for w in waves])
+        lab = None
+        n_classes = 0
+        if labels is not None:
+            lab = np.ascontiguousarray(labels, np.float32)
+            assert lab.shape[0] == len(waves)
+            n_classes = lab.shape[1]
+        L.check(self.lib.iris_bank_register(
+            self._ctx, kind, len(waves), n_chan, packed.ctypes.data, offsets.ctypes.data,
+            lab.ctypes.data if lab is not None else None, n_classes, int(bool(normalize)),
+            self._stream()))
+        frames = np.zeros(len(waves), np.int32)
+        L.check(self.lib.iris_bank_info(self._ctx, kind, None, None, frames.ctypes.data))
+        self.bank_frames[kind] = frames
+        self.bank_chan = n_chan
+        if kind == L.BANK_VOICE:
+            self.n_classes = n_classes
+        return frames
+
+    def voice_activity(self, item):
+        n = int(self.bank_frames[L.BANK_VOICE][item])
+        out = np.zeros(n, np.uint8)
+        L.check(self.lib.iris_bank_activity(self._ctx, int(item), out.ctypes.data))
+        return out
+
+    # ---- per-step ----
+    def upload_plan(self, d: BatchDraws, stft_filter=0, chan_remap=L.REMAP_NONE, n_out_chan=0):
+        def i32(a):
+            return None if a is None else np.ascontiguousarray(a, np.int32)
+
+        def f32(a):
+            return None if a is None else np.ascontiguousarray(a, np.float32)
+
+        keep = dict(bg_id=i32(d.bg_id), bg_offset=i32(d.bg_offset), n_voices=i32(d.n_voices),
+                    voice_id=i32(d.voice_id), voice_gain=f32(d.voice_gain),
+                    voice_offset=i32(d.voice_offset), n_noises=i32(d.n_noises),
+                    noise_id=i32(d.noise_id), noise_gain=f32(d.noise_gain),
+                    noise_offset=i32(d.noise_offset), time_masks=i32(d.time_masks),
+                    freq_masks=i32(d.freq_masks), merge_factor=f32(d.merge_factor))
+        p = L.IrisPlan()
+        p.batch, p.n_frame = int(d.batch), int(d.n_frame)
+        p.max_voices, p.max_noises = int(d.max_voices), int(d.max_noises)
+        p.min_ratio, p.min_noise_ratio = float(d.min_ratio), float(d.min_noise_ratio)
+        for k, v in keep.items():
+            if v is None:
+                continue
+            ptr_t = L._f32p if v.dtype == np.float32 else L._i32p
+            setattr(p, k, v.ctypes.data_as(ptr_t))
+        p.n_time_masks = 0 if d.time_masks is None else d.time_masks.shape[1]
+        p.n_freq_masks = 0 if d.freq_masks is None else d.freq_masks.shape[1]
+        p.stft_filter = int(stft_filter)
+        p.chan_remap = int(chan_remap)
+        p.n_out_chan = int(n_out_chan)
+        L.check(self.lib.iris_plan_upload(self._ctx, C.byref(p), self._stream()))
+        c_out = self.bank_chan
+        if chan_remap == L.REMAP_STEREO_MONO:
+            c_out = 3
+        elif chan_remap == L.REMAP_MERGE_AUG:
+            c_out = int(n_out_chan)
+        self._plan = dict(B=int(d.batch), T=int(d.n_frame), V=int(d.max_voices), c_out=c_out,
+                          bytes=sum(v.nbytes for v in keep.values() if v is not None))
+        return self._plan
+
+    def labels(self, want_vtk=False, want_keep=True):
+        """-> (frame_labels [B,T,K], labels [B,V,T,K] or None, keep [B,V] uint8 or None)."""
+        torch = _torch()
+        pl = self._plan
+        B, T, V, K = pl['B'], pl['T'], pl['V'], self.n_classes
+        if V == 0:
+            raise ValueError('the uploaded plan has no voices, hence no labels')
+        frame = self._empty((B, T, K))
+        vtk = self._empty((B, V, T, K)) if want_vtk else None
+        keep = self._empty((B, V), torch.uint8) if want_keep else None
+        L.check(self.lib.iris_labels(self._ctx, self._ptr(vtk), self._ptr(frame),
+                                     self._ptr(keep), self._stream()))
+        return frame, vtk, keep
+
+    def feature_shape(self, mode):
+        pl = self._plan
+        if mode >= L.FEAT_MEL:
+            return (pl['B'], self.n_mel, pl['T'], self.bank_chan)
+        return (pl['B'], 257, pl['T'], 2 * pl['c_out'])
+
+    def features(self, mode, out=None):
+        shape = self.feature_shape(mode)
+        if out is None:
+            out = self._empty(shape)
+        else:
+            assert tuple(out.shape) == shape and out.is_contiguous() and out.is_cuda
+        L.check(self.lib.iris_features(self._ctx, int(mode), self._ptr(out), self._stream()))
+        return out
+
+    def plan_bytes(self, mode, keep=None):
+        bi, bo = C.c_int64(), C.c_int64()
+        k = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+        L.check(self.lib.iris_plan_bytes(self._ctx, int(mode),
+                                         k.ctypes.data if k is not None else None,
+                                         C.byref(bi), C.byref(bo)))
+        return bi.value, bo.value
+
+    def profile(self, enable=True):
+        L.check(self.lib.iris_profile_enable(self._ctx, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        """-> (summed device ms of the fused-kernel launches, number of launches)."""
+        ms, n = C.c_double(), C.c_int32()
+        L.check(self.lib.iris_profile_read(self._ctx, C.byref(ms), C.byref(n), int(bool(reset))))
+        return ms.value, n.value
+
+    def stft(self, wav, normalize=True):
+        """``load_wav`` on an in-memory waveform ``[C, N]`` -> ``[257, T, 2C]`` (device)."""
+        torch = _torch()
+        if isinstance(wav, torch.Tensor):
+            w = wav.to(torch.float32).contiguous()
+            ptr = w.data_ptr()
+        else:
+            w = np.ascontiguousarray(wav, np.float32)
+            ptr = w.ctypes.data
+        n_chan, n = w.shape
+        out = self._empty((257, 1 + n // 256, 2 * n_chan))
+        L.check(self.lib.iris_stft(self._ctx, C.c_void_p(ptr), n_chan, n, int(bool(normalize)),
+                                   self._ptr(out), self._stream()))
+        return out
+
+    def metric_counts(self, y_true, y_pred, threshold=0.5, tpfpfn=None, want_er=True):
+        """-> (triples [B,3] int32, tpfpfn [3] int64 accumulated, er [B] float or None)."""
+        torch = _torch()
+        yt = torch.as_tensor(y_true, dtype=torch.float32, device=self.device).contiguous()
+        yp = torch.as_tensor(y_pred, dtype=torch.float32, device=self.device).contiguous()
+        B, T, K = yt.shape
+        assert yp.shape == yt.shape
+        triples = self._empty((B, 3), torch.int32)
+        if tpfpfn is None:
+            tpfpfn = torch.zeros(3, dtype=torch.int64, device=self.device)
+        er = self._empty((B,)) if want_er else None
+        L.check(self.lib.iris_metric_counts(self._ctx, self._ptr(yt), self._ptr(yp), B, T, K,
+                                            float(threshold), self._ptr(triples),
+                                            self._ptr(tpfpfn), self._ptr(er), self._stream()))
+        return triples, tpfpfn, er
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine of a device (default: torch's current CUDA device)."""
+    torch = _torch()
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    device = int(device)
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

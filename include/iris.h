@@ -1,0 +1,152 @@
+/* libiris -- C ABI of the B200-native preprocessing hot path of IRIS-AUDIO/challenge.
+ *
+ * The reference has no FFI: its boundary is the Python function surface of pipeline.py,
+ * transforms.py, data_utils.py and metrics.py, consumed as tf.data map callables and Keras
+ * metric callables.  This header is what a maintainer's binding (ctypes / a TF custom op /
+ * cffi) calls instead; every entry point names the reference code it replaces.  Plain
+ * pointers and sizes only; device buffers are CALLER-allocated (framework allocator) and
+ * handed over as raw pointers (DLPack `data` + `byte_offset`), outputs are written in the
+ * reference's layouts, all work is enqueued on the caller's CUDA stream.  Return 0 on
+ * success, a negative IRIS_ERR_* otherwise; iris_last_error() gives the thread-local text.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * One context per device; calls on one context are serialised by the caller.
+ */
+#ifndef IRIS_H_
+#define IRIS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRIS_ABI_VERSION 1
+
+typedef struct iris_ctx iris_ctx;
+typedef void* iris_stream; /* cudaStream_t */
+
+enum {
+    IRIS_OK = 0,
+    IRIS_ERR_INVALID = -1,     /* bad argument (reference: assert / ValueError) */
+    IRIS_ERR_CUDA = -2,        /* CUDA runtime error, text in iris_last_error() */
+    IRIS_ERR_EMPTY_RANGE = -3, /* reference: tf InvalidArgumentError on int-uniform with
+                                  maxval <= minval (pipeline.py:68-69) */
+    IRIS_ERR_STATE = -4,       /* call order (no plan / bank not registered) */
+    IRIS_ERR_UNSUPPORTED = -5  /* valid in the reference, outside the fused path */
+};
+
+enum { IRIS_BANK_BG = 0, IRIS_BANK_VOICE = 1, IRIS_BANK_NOISE = 2 };
+
+/* feature modes of iris_features(); layouts as in the reference */
+enum {
+    IRIS_FEAT_COMPLEX = 0,       /* [B,257,T,2C']  make_pipeline output (pipeline.py:131-133)  */
+    IRIS_FEAT_MAGPHASE = 1,      /* [B,257,T,2C']  complex_to_magphase (transforms.py:111-123)  */
+    IRIS_FEAT_LOG_MAGPHASE = 2,  /* [B,257,T,2C']  + log_magphase (transforms.py:80-86)         */
+    IRIS_FEAT_MEL = 3,           /* [B,n_mel,T,C'] magphase_to_mel (transforms.py:51-77)        */
+    IRIS_FEAT_LOGMEL = 4,        /* [B,n_mel,T,C'] + log_on_mel ('nominmax', sj_train.py:121)   */
+    IRIS_FEAT_LOGMEL_MINMAX = 5  /* [B,n_mel,T,C'] + minmax + log_on_mel (sj_train.py:119-123)  */
+};
+
+enum { IRIS_REMAP_NONE = 0, IRIS_REMAP_STEREO_MONO = 1, IRIS_REMAP_MERGE_AUG = 2 };
+
+int iris_abi_version(void);
+const char* iris_last_error(void);
+
+int iris_ctx_create(int device, iris_ctx** out);
+int iris_ctx_destroy(iris_ctx* ctx);
+
+/* Mel weights: dense [n_bins=257, n_mel] row-major host array, i.e. the matrix
+ * tf.signal.linear_to_mel_weight_matrix returns at transforms.py:55-56.  Stored sparse. */
+int iris_set_mel(iris_ctx* ctx, int n_mel, int n_bins, const float* dense_w);
+
+/* Register a bank of WAVEFORMS (replaces data_utils.load_wav, data_utils.py:9-29, for every
+ * source: normalize (32-34) + reflect padding now, STFT inside iris_features).
+ *   packed_wav : item i is the [n_chan, len_i] row-major block starting at float
+ *                n_chan * offsets[i]; host or device pointer.
+ *   offsets    : [n_items+1] cumulative per-channel sample counts (host).
+ *   labels     : [n_items, n_classes] host floats (one-hot rows) for the VOICE bank, else NULL.
+ * For the VOICE bank the per-frame activity flags (reduce_max(voice) > 0, pipeline.py:55)
+ * are computed here by one STFT pass.  Synchronises the stream before returning. */
+int iris_bank_register(iris_ctx* ctx, int kind, int n_items, int n_chan, const float* packed_wav,
+                       const int64_t* offsets, const float* labels, int n_classes, int normalize,
+                       iris_stream stream);
+int iris_bank_info(iris_ctx* ctx, int kind, int32_t* n_items, int32_t* n_chan,
+                   int32_t* n_frames /* [n_items] or NULL */);
+int iris_bank_activity(iris_ctx* ctx, int item, uint8_t* host_out /* [n_frames[item]] */);
+
+/* All random draws of one batch, made by the HOST in the reference's draw order
+ * (SURVEY.md 3.1): everything tf.random supplies inside merge_complex_specs
+ * (pipeline.py:35,43,50,69,87,94,103), mask (transforms.py:25-26) and random_merge_aug
+ * (data_utils.py:109).  Arrays are host pointers, row-major. */
+typedef struct iris_plan {
+    int32_t batch;        /* B */
+    int32_t n_frame;      /* T   (make_pipeline n_frame)                                   */
+    int32_t max_voices;   /* V   padded_batch group size (pipeline.py:155); 0 = no voices  */
+    int32_t max_noises;   /* M   (pipeline.py:165); 0 = no noises                          */
+    float min_ratio;      /* merge_complex_specs min_ratio (sj_train passes 1)             */
+    float min_noise_ratio;
+    const int32_t* bg_id;        /* [B]                                                    */
+    const int32_t* bg_offset;    /* [B]   random_crop offset into the tiled background     */
+    const int32_t* n_voices;     /* [B]   in [1, V)  (V == 1: 1)                           */
+    const int32_t* voice_id;     /* [B,V] the whole group (its longest member pads all)    */
+    const float* voice_gain;     /* [B,V] pow(10, -u), u ~ U[0, -snr/10)                   */
+    const int32_t* voice_offset; /* [B,V] in [0, len - T)                                  */
+    const int32_t* n_noises;     /* [B]   in [0, M)                                        */
+    const int32_t* noise_id;     /* [B,M]                                                  */
+    const float* noise_gain;     /* [B,M] pow(10, -u), u ~ U[0, 2)                         */
+    const int32_t* noise_offset; /* [B,M] in [0, len - T]                                  */
+    int32_t n_time_masks;        /* augment: 6 (data_utils.py:59)                          */
+    int32_t n_freq_masks;        /* augment: 1 (data_utils.py:60)                          */
+    const int32_t* time_masks;   /* [B,n_time_masks,2] (size, offset) or NULL              */
+    const int32_t* freq_masks;   /* [B,n_freq_masks,2] (size, offset) or NULL              */
+    int32_t stft_filter;         /* zero bins 1..k (data_utils.py:126-136); 0 = off        */
+    int32_t chan_remap;          /* IRIS_REMAP_*  (data_utils.py:79-82, 100-117)           */
+    int32_t n_out_chan;          /* channels after remap (3 for stereo_mono)               */
+    const float* merge_factor;   /* [B, n_out_chan-2] U(0.1, 0.9), REMAP_MERGE_AUG only    */
+} iris_plan;
+
+/* Validates the draws against the registered banks with the reference's placement
+ * arithmetic (pipeline.py:29-35, 58-74, 95-103) and uploads the batch plan. */
+int iris_plan_upload(iris_ctx* ctx, const iris_plan* plan, iris_stream stream);
+
+/* Labels of merge_complex_specs (pipeline.py:41-84): same-class overlap rejection and
+ * per-voice frame labels, then to_frame_labels (data_utils.py:64-70).
+ *   d_labels_vtk   : [B,V,T,K] float or NULL      (make_pipeline's label output)
+ *   d_frame_labels : [B,T,K]   float or NULL      (after to_frame_labels)
+ *   d_keep         : [B,V]     uint8 or NULL      (no_overlap flag per voice slot) */
+int iris_labels(iris_ctx* ctx, float* d_labels_vtk, float* d_frame_labels, uint8_t* d_keep,
+                iris_stream stream);
+
+/* The fused feature kernel for the uploaded plan; d_out sized per the mode's layout. */
+int iris_features(iris_ctx* ctx, int mode, float* d_out, iris_stream stream);
+
+/* data_utils.load_wav on one in-memory waveform (data_utils.py:9-29 minus decode/resample):
+ * wav [n_chan, n_samples] (host or device) -> d_out [257, 1 + n_samples/256, 2*n_chan]. */
+int iris_stft(iris_ctx* ctx, const float* wav, int n_chan, int64_t n_samples, int normalize,
+              float* d_out, iris_stream stream);
+
+/* metrics.er_score(smoothing=False) integer core (metrics.py:217-266) and tfa F1Score
+ * micro counts (metrics.py:290-298) for y_true, y_pred [B,T,K] device floats.
+ *   d_triples : [B,3] int32  (n_true, n_pred, correct)
+ *   d_tpfpfn  : [3]   uint64 ACCUMULATED (the reference's F1 metric is never reset), or NULL
+ *   d_er      : [B]   float  score per sample (metrics.py:268-273), or NULL */
+int iris_metric_counts(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred, int batch,
+                       int n_frame, int n_classes, float threshold, int32_t* d_triples,
+                       uint64_t* d_tpfpfn, float* d_er, iris_stream stream);
+
+/* Algorithmic HBM bytes of the last uploaded plan for `mode`: 4 * (samples of
+ * every kept source frame range read + output elements); used by bench.py's roofline. */
+int iris_plan_bytes(iris_ctx* ctx, int mode, const uint8_t* host_keep, int64_t* bytes_in,
+                    int64_t* bytes_out);
+
+/* Measurement hook for bench.py's roofline: when enabled, every launch of the fused
+ * feature kernel inside iris_features() is bracketed by cudaEvents on the launching stream;
+ * iris_profile_read() synchronises them and returns the summed device time. */
+int iris_profile_enable(iris_ctx* ctx, int enable);
+int iris_profile_read(iris_ctx* ctx, double* total_ms, int32_t* n_launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRIS_H_ */

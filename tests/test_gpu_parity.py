@@ -1,0 +1,231 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same
+seeded inputs and the same host draws.  Bars (BASELINE.json north_star): bit-exact masks /
+labels / keep flags / metric counts; float features within normalised max error 1e-4
+(max|a-b| / max|b|); phase as circular error gated on magnitude."""
+import numpy as np
+import pytest
+
+from conftest import nmax_err, phase_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _draw(w, B, T, C_remap=0, seed=0, masks=True, V=7, M=2, min_ratio=1, merge_extra=0):
+    from challenge_b200.plan import draw_batch
+    rng = np.random.default_rng(seed)
+    return draw_batch(rng, B, T, w.bg_frames, w.voice_frames, w.noise_frames, max_voices=V,
+                      max_noises=M, snr=-20, min_ratio=min_ratio,
+                      n_time_masks=6 if masks else 0, n_freq_masks=1 if masks else 0,
+                      merge_extra=merge_extra)
+
+
+def _oracle(w, d, **kw):
+    from oracle import chain
+    return chain.dataset_batch(w.o_bg, w.o_voice, w.labels, w.o_noise, d, **kw)
+
+
+def test_stft_matches_reference_call(engine):
+    """load_wav (data_utils.py:9-29): normalize + Spectrogram(512) + [F,T,2C] layout."""
+    from oracle import data_utils as D
+    rng = np.random.default_rng(3)
+    for C, N in [(2, 160000), (4, 40000), (1, 5000), (3, 12345), (2, 257)]:
+        wav = (rng.standard_normal((C, N)) * 0.1).astype(np.float32)
+        got = engine.stft(wav).cpu().numpy()
+        ref = D.load_wav_array(wav)
+        assert got.shape == ref.shape == (257, 1 + N // 256, 2 * C)
+        assert nmax_err(got, ref) < TOL
+        # DC and Nyquist imaginary parts are exactly +0.0 like torch.stft
+        assert not np.any(got[0, :, C:]) and not np.any(np.signbit(got[0, :, C:]))
+        assert not np.any(got[256, :, C:]) and not np.any(np.signbit(got[256, :, C:]))
+    got = engine.stft(wav, normalize=False).cpu().numpy()
+    assert nmax_err(got, D.load_wav_array(wav, do_normalize=False)) < TOL
+
+
+def test_voice_activity_bit_exact(engine, workload_factory):
+    """pipeline.py:55 -- frame active iff any STFT coefficient > 0."""
+    w = workload_factory(2)
+    for i in range(len(w.voices)):
+        assert np.array_equal(engine.voice_activity(i), w.o_voice.activity(i)), i
+    assert any(0 in engine.voice_activity(i) for i in range(len(w.voices)))
+
+
+def test_cfg1_logmel_no_augmentation(engine, workload_factory):
+    """BASELINE config 1: 2-ch 10 s clips -> log-mel, no voices / noises / masks."""
+    from challenge_b200 import _lib as L
+    from challenge_b200.plan import draw_batch
+    w = workload_factory(2)
+    d = draw_batch(np.random.default_rng(1), 4, 626, w.bg_frames)
+    engine.upload_plan(d)
+    for mode, name in [(L.FEAT_MEL, 'mel'), (L.FEAT_LOGMEL, 'logmel'),
+                       (L.FEAT_LOGMEL_MINMAX, 'logmel_minmax')]:
+        got = engine.features(mode).cpu().numpy()
+        ref, _, _, _ = _oracle(w, d, mode=name)
+        assert got.shape == ref.shape == (4, 80, 626, 2)
+        assert nmax_err(got, ref) < TOL, name
+
+
+@pytest.mark.parametrize('T', [626, 512, 100])
+def test_cfg2_mix_masks_labels(engine, workload_factory, T):
+    """BASELINE config 2: noise mixing at sampled SNR + time/freq masks + labels."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    d = _draw(w, 8, T, seed=T)
+    engine.upload_plan(d)
+    frame, vtk, keep = engine.labels(want_vtk=True)
+    ref_c, ref_y, ref_vtk, ref_keep = _oracle(w, d, mode='complex')
+    assert np.array_equal(keep.cpu().numpy(), np.stack(ref_keep))
+    assert np.array_equal(frame.cpu().numpy(), ref_y)
+    assert np.array_equal(vtk.cpu().numpy(), np.stack(ref_vtk))
+    got_c = engine.features(L.FEAT_COMPLEX).cpu().numpy()
+    assert got_c.shape == ref_c.shape
+    assert nmax_err(got_c, ref_c) < TOL
+    # masks are exact zeros in exactly the same cells
+    assert np.array_equal(got_c == 0, ref_c == 0)
+    for mode, name in [(L.FEAT_MEL, 'mel'), (L.FEAT_LOGMEL_MINMAX, 'logmel_minmax')]:
+        got = engine.features(mode).cpu().numpy()
+        ref = _oracle(w, d, mode=name)[0]
+        assert nmax_err(got, ref) < TOL, name
+
+
+def test_cfg3_four_channel_magphase_labels(engine, workload_factory):
+    """BASELINE config 3: 4-ch clips, magnitude + phase features and frame labels."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(4, seed=20203, n_bg=2, n_voice=16, n_noise=4)
+    d = _draw(w, 4, 626, seed=33)
+    engine.upload_plan(d)
+    frame, _, keep = engine.labels()
+    ref, ref_y, _, ref_keep = _oracle(w, d, mode='magphase')
+    assert np.array_equal(frame.cpu().numpy(), ref_y)
+    assert np.array_equal(keep.cpu().numpy(), np.stack(ref_keep))
+    got = engine.features(L.FEAT_MAGPHASE).cpu().numpy()
+    assert got.shape == ref.shape == (4, 257, 626, 8)
+    assert nmax_err(got[..., :4], ref[..., :4]) < TOL
+    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    got = engine.features(L.FEAT_LOG_MAGPHASE).cpu().numpy()
+    ref = _oracle(w, d, mode='log_magphase')[0]
+    sel = ref[..., :4] > np.log(1e-3 * np.exp(ref[..., :4].max()))
+    assert np.abs(got[..., :4][sel] - ref[..., :4][sel]).max() < 1e-2
+    got = engine.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy()
+    assert nmax_err(got, _oracle(w, d, mode='logmel_minmax')[0]) < TOL
+
+
+def test_background_tiling_and_short_banks(engine, workload_factory):
+    """Backgrounds shorter than n_frame are tiled then cropped (pipeline.py:29-35)."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(2, seed=7, n_bg=3, n_voice=12, n_noise=4, bg_seconds=1.7)
+    d = _draw(w, 6, 300, seed=5, min_ratio=2 / 3)
+    engine.upload_plan(d)
+    frame, _, keep = engine.labels()
+    ref, ref_y, _, ref_keep = _oracle(w, d, mode='complex')
+    assert np.array_equal(frame.cpu().numpy(), ref_y)
+    assert np.array_equal(keep.cpu().numpy(), np.stack(ref_keep))
+    assert nmax_err(engine.features(L.FEAT_COMPLEX).cpu().numpy(), ref) < TOL
+
+
+def test_channel_remaps_and_filter(engine, workload_factory):
+    """stereo_mono / random_merge_aug / stft_filter (data_utils.py:79-136) fused in the epilogue."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    d = _draw(w, 3, 200, seed=11, merge_extra=2)
+    engine.upload_plan(d, stft_filter=3, chan_remap=L.REMAP_STEREO_MONO)
+    got = engine.features(L.FEAT_COMPLEX).cpu().numpy()
+    ref = _oracle(w, d, mode='complex', remap='stereo_mono', stft_filter=3)[0]
+    assert got.shape == ref.shape == (3, 257, 200, 6)
+    assert nmax_err(got, ref) < TOL
+    assert not np.any(got[:, 1:4])
+    engine.upload_plan(d, chan_remap=L.REMAP_MERGE_AUG, n_out_chan=4)
+    got = engine.features(L.FEAT_MAGPHASE).cpu().numpy()
+    ref = _oracle(w, d, mode='magphase', remap='merge_aug', n_out_chan=4)[0]
+    assert got.shape == ref.shape == (3, 257, 200, 8)
+    assert nmax_err(got[..., :4], ref[..., :4]) < TOL
+    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+
+
+def test_empty_offset_range_raises_like_reference(engine, workload_factory):
+    """pipeline.py:68-69: int-uniform with maxval == 0 raises when the padded voice length
+    equals n_frame with min_ratio=1."""
+    from challenge_b200.errors import InvalidArgumentError
+    w = workload_factory(2)
+    d = _draw(w, 2, 626, seed=2)
+    d.n_frame = int(w.voice_frames[d.voice_id[0]].max())
+    d.bg_offset[:] = 0
+    with pytest.raises(InvalidArgumentError):
+        engine.upload_plan(d)
+
+
+def _blocky(rng, B, T, K, p=0.4):
+    y = np.zeros((B, T, K), np.float32)
+    for b in range(B):
+        for c in range(K):
+            t = 0
+            while t < T:
+                n = int(rng.integers(1, 60))
+                if rng.random() < p:
+                    y[b, t:t + n, c] = 1
+                t += n
+    return y
+
+
+def test_metric_counts_bit_exact(engine):
+    """er_score / f1_score counting (metrics.py:217-298) incl. the reference's golden ER."""
+    from oracle import metrics as M
+    # golden: metrics_test.py:12-25  => mean ER == 1.2
+    gt = [[0, 0, 10], [2, 0, 20], [1, 15, 30], [2, 31, 40], [1, 32, 35]]
+    pr = [[1, 5], [1, 19], [2, 32], [2, 38], [0, 38]]
+    g = np.zeros([2, 40, 3], np.float32)
+    p = np.zeros([2, 40, 3], np.float32)
+    for c, s, e in gt:
+        g[:, s:e, c] = 1
+    for c, t in pr:
+        p[:, t - 2:t + 2, c] = 1
+    triples, _, er = engine.metric_counts(g, p)
+    assert triples.cpu().numpy().tolist() == [[5, 5, 2], [5, 5, 2]]
+    assert float(er.cpu().numpy().mean()) == np.float32(1.2)
+    rng = np.random.default_rng(0)
+    for (B, T) in [(64, 626), (7, 33), (3, 1), (16, 512), (5, 31), (5, 32)]:
+        yt = _blocky(rng, B, T, 3)
+        yp = np.clip(yt + rng.normal(0, 0.35, yt.shape), 0, 1).astype(np.float32)
+        triples, tpfpfn, er = engine.metric_counts(yt, yp)
+        nt, npd, co = M.er_parts(yt, yp)
+        assert np.array_equal(triples.cpu().numpy(), np.stack([nt, npd, co], 1))
+        assert tuple(tpfpfn.cpu().numpy().tolist()) == M.f1_counts(yt, yp)
+        ref_er = M.er_from_parts(nt, npd, co)
+        assert np.array_equal(er.cpu().numpy(), ref_er, equal_nan=True)
+    # F1 state accumulates across calls (metrics.py:291-297 closure)
+    triples, tpfpfn, _ = engine.metric_counts(yt, yp, tpfpfn=tpfpfn)
+    assert tuple(tpfpfn.cpu().numpy().tolist()) == tuple(2 * v for v in M.f1_counts(yt, yp))
+
+
+def test_full_size_properties_cfg2(engine, workload_factory):
+    """BASELINE config 2 at full batch (256): size-independent properties + spot parity."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    B = 256
+    d = _draw(w, B, 626, seed=2024)
+    engine.upload_plan(d)
+    frame, vtk, keep = engine.labels(want_vtk=True)
+    x = engine.features(L.FEAT_LOGMEL_MINMAX)
+    x2 = engine.features(L.FEAT_LOGMEL_MINMAX)
+    assert bool((x == x2).all()), 'not deterministic'
+    xn = x.cpu().numpy()
+    assert xn.shape == (B, 80, 626, 2) and np.isfinite(xn).all()
+    # min-max then log: every clip spans exactly [log(1e-8), log(1 + 1e-8)]
+    assert np.all(xn.reshape(B, -1).min(1) == np.log(np.float32(1e-8)))
+    assert np.allclose(xn.reshape(B, -1).max(1), 0, atol=1e-6)
+    # time-masked frames are the clip minimum everywhere
+    for b in range(0, B, 37):
+        for size, off in d.time_masks[b]:
+            assert np.all(xn[b, :, off:off + size] == np.log(np.float32(1e-8)))
+    fr = frame.cpu().numpy()
+    assert set(np.unique(fr)) <= {0.0, 1.0}
+    assert np.array_equal(vtk.cpu().numpy().sum(1), fr)
+    kp = keep.cpu().numpy()
+    assert np.all(kp[:, 0] == 1)          # the first voice can never collide
+    assert not kp[np.arange(7)[None, :] >= d.n_voices[:, None]].any()
+    clips = [0, 101, 255]
+    ref, ref_y, _, ref_keep = _oracle(w, d, mode='logmel_minmax', clips=clips)
+    assert nmax_err(xn[clips], ref) < TOL
+    assert np.array_equal(fr[clips], ref_y)
+    assert np.array_equal(kp[clips], np.stack(ref_keep))
