@@ -70,12 +70,16 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
         }
         if (C == 2) {
             *reinterpret_cast<float4*>(o) = make_float4(a0, a1, b0, b1);
-        } else if (has1) {
+        } else if (has1 && (C & 1) == 0) {
             *reinterpret_cast<float2*>(o + 2 * pair) = make_float2(a0, a1);
             *reinterpret_cast<float2*>(o + C + 2 * pair) = make_float2(b0, b1);
         } else {
             o[2 * pair] = a0;
             o[C + 2 * pair] = b0;
+            if (has1) {
+                o[2 * pair + 1] = a1;
+                o[C + 2 * pair + 1] = b1;
+            }
         }
     } else {
         // C == 2 input; c_out output channels (data_utils.py:79-82, 100-117)
