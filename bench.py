@@ -359,18 +359,19 @@ def run_gpu_arm(args):
         h2d = info['bytes']
         d2h = h_feat.numel() * 4 + h_lbl.numel() * 4 + h_cnt.numel() * 8
 
-    for _ in range(max(args.warmup, 3)):
+    n_e2e = 0 if args.no_e2e else args.steps
+    for _ in range(0 if args.no_e2e else max(args.warmup, 3)):
         e2e_step()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         e2e_step()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
+    e2e_value = world * B * n_e2e / float(t.item())
 
     peak, peak_src = measured_peak()
     fused_avg_ms = fused_ms / max(n_fused, 1)
@@ -432,6 +433,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
