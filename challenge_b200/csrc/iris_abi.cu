@@ -74,8 +74,8 @@ struct iris_ctx {
     Bank banks[3];
     DevBuf tw, whalf;
     // mel (CSR by mel bin)
-    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0;
-    DevBuf mel_ptr, mel_f, mel_w;
+    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_nw = 0;
+    DevBuf mel_info, mel_w;
     // plan
     bool has_plan = false, labels_done = false;
     int B = 0, T = 0, V = 0, M = 0, C = 0;
@@ -83,7 +83,7 @@ struct iris_ctx {
     std::vector<Seg> h_segs;
     std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
     std::vector<int32_t> h_seg_ptr;
-    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;
+    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
     void* h_stage = nullptr;  // pinned staging for the plan blob
     size_t h_stage_cap = 0;
     cudaEvent_t stage_free = nullptr;
@@ -106,13 +106,15 @@ int set_device(iris_ctx* c) {
 }
 
 int build_tables(iris_ctx* c) {
-    std::vector<float> tw(2 * 512), wh(512);
-    for (int k1 = 0; k1 < 32; ++k1)
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const double a = -2.0 * M_PI * double(k1 * n2) / 512.0;
-            tw[2 * (k1 * 16 + n2)] = float(cos(a));
-            tw[2 * (k1 * 16 + n2) + 1] = float(sin(a));
-        }
+    // inter-pass twiddles W512^(n2*k1), two k1 per float4: [m][n2] = {k1 = 2m, k1 = 2m + 1}
+    std::vector<float> tw(4 * 256), wh(512);
+    for (int m = 0; m < 16; ++m)
+        for (int n2 = 0; n2 < 16; ++n2)
+            for (int h = 0; h < 2; ++h) {
+                const double a = -2.0 * M_PI * double((2 * m + h) * n2) / 512.0;
+                tw[4 * (m * 16 + n2) + 2 * h] = float(cos(a));
+                tw[4 * (m * 16 + n2) + 2 * h + 1] = float(sin(a));
+            }
     // periodic Hann (torch.hann_window(512)), pre-scaled by the 1/2 of the two-channel split
     for (int n = 0; n < 512; ++n) wh[n] = float(0.5 * (0.5 - 0.5 * cos(2.0 * M_PI * n / 512.0)));
     CU(c->tw.reserve(tw.size() * 4));
@@ -124,14 +126,25 @@ int build_tables(iris_ctx* c) {
 
 void fill_common(iris_ctx* c, FusedParams& p) {
     memset(&p, 0, sizeof(p));
-    p.tw = c->tw.as<float2>();
+    p.tw4 = c->tw.as<float4>();
     p.whalf = c->whalf.as<float>();
     p.n_mel = c->n_mel;
     p.mel_f_lo = c->mel_f_lo;
     p.mel_f_n = c->mel_f_n;
-    p.mel_ptr = c->mel_ptr.as<int32_t>();
-    p.mel_f = c->mel_f.as<int16_t>();
+    p.mel_nw = c->mel_nw;
+    p.mel_info = c->mel_info.as<uint32_t>();
     p.mel_w = c->mel_w.as<float>();
+}
+
+// tile shape of the fused kernel: NP channel pairs x 16/NP frames
+void set_geometry(FusedParams& p, int n_chan) {
+    p.C = n_chan;
+    p.n_pairs = (n_chan + 1) / 2;
+    int sh = 0;
+    while ((1 << sh) < p.n_pairs && sh < 4) ++sh;
+    p.np_shift = sh;
+    p.n_groups = (p.n_pairs + (1 << sh) - 1) >> sh;
+    p.c_out = n_chan;
 }
 
 int ensure_stage(iris_ctx* c, size_t bytes) {
@@ -244,7 +257,7 @@ int iris_ctx_destroy(iris_ctx* c) {
     for (auto& b : c->banks) {
         b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
     }
-    for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_ptr, &c->mel_f, &c->mel_w, &c->plan_blob, &c->keep,
+    for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
                       &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -257,37 +270,35 @@ int iris_ctx_destroy(iris_ctx* c) {
 int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     if (!c || !w) return fail(IRIS_ERR_INVALID, "NULL argument");
     if (n_bins != kBins) return fail(IRIS_ERR_INVALID, "n_bins must be 257 (n_fft 512)");
-    if (n_mel < 1 || n_mel > 256) return fail(IRIS_ERR_INVALID, "n_mel must be in [1, 256]");
+    if (n_mel < 1 || n_mel > 128) return fail(IRIS_ERR_INVALID, "n_mel must be in [1, 128]");
     int rc = set_device(c);
     if (rc) return rc;
-    std::vector<int32_t> ptr(n_mel + 1, 0);
-    std::vector<int16_t> fi;
+    // every mel filter is stored as the contiguous bin range [start, start + len) that holds
+    // its non-zero weights (the triangles of linear_to_mel_weight_matrix are contiguous)
+    std::vector<uint32_t> info(n_mel, 0);
     std::vector<float> fw;
     int f_lo = kBins, f_hi = -1;
     for (int m = 0; m < n_mel; ++m) {
-        for (int f = 0; f < n_bins; ++f) {
-            const float v = w[size_t(f) * n_mel + m];
-            if (v != 0.f) {
-                fi.push_back(int16_t(f));
-                fw.push_back(v);
-                if (f < f_lo) f_lo = f;
-                if (f > f_hi) f_hi = f;
+        int lo = -1, hi = -1;
+        for (int f = 0; f < n_bins; ++f)
+            if (w[size_t(f) * n_mel + m] != 0.f) {
+                if (lo < 0) lo = f;
+                hi = f;
             }
-        }
-        ptr[m + 1] = int32_t(fi.size());
+        if (lo < 0) continue;   // empty filter: len 0
+        if (fw.size() + size_t(hi - lo + 1) >= (1u << 14))
+            return fail(IRIS_ERR_UNSUPPORTED, "mel matrix too dense for the fused projection");
+        info[m] = uint32_t(lo) | (uint32_t(hi - lo + 1) << 9) | (uint32_t(fw.size()) << 18);
+        for (int f = lo; f <= hi; ++f) fw.push_back(w[size_t(f) * n_mel + m]);
+        f_lo = std::min(f_lo, lo);
+        f_hi = std::max(f_hi, hi);
     }
     if (f_hi < 0) { f_lo = 0; f_hi = 0; }
-    if (f_hi - f_lo + 1 > fused_max_mel_window())
-        return fail(IRIS_ERR_UNSUPPORTED,
-                    "mel matrix support spans more than 136 bins; use the unfused mel projection");
-    CU(c->mel_ptr.reserve(ptr.size() * 4));
-    CU(c->mel_f.reserve(fi.size() * 2 + 2));
+    CU(c->mel_info.reserve(info.size() * 4));
     CU(c->mel_w.reserve(fw.size() * 4 + 4));
-    CU(cudaMemcpy(c->mel_ptr.p, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
-    if (!fi.empty()) {
-        CU(cudaMemcpy(c->mel_f.p, fi.data(), fi.size() * 2, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
-    }
+    CU(cudaMemcpy(c->mel_info.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice));
+    if (!fw.empty()) CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
+    c->mel_nw = int(fw.size());
     c->n_mel = n_mel;
     c->mel_f_lo = f_lo;
     c->mel_f_n = f_hi - f_lo + 1;
@@ -324,11 +335,10 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         if (kT > b.max_frames) b.max_frames = int(kT);
         b.pad_offsets[i + 1] = b.pad_offsets[i] + 256 * (kT + 1);
     }
-    for (int k = 0; k < 3; ++k)
-        if (k != kind && c->banks[k].ready && c->banks[k].n_chan != n_chan)
-            return fail(IRIS_ERR_INVALID, "all banks must have the same channel count");
+    if (n_chan > 32) return fail(IRIS_ERR_UNSUPPORTED, "more than 32 channels");
+    const int n_pairs = (n_chan + 1) / 2;
     const size_t wav_floats = size_t(offsets[n_items]) * n_chan;
-    const size_t pad_floats = size_t(b.pad_offsets[n_items]) * n_chan;
+    const size_t pad_floats = size_t(b.pad_offsets[n_items]) * n_pairs * 2;
     DevBuf raw, d_off;
     CU(raw.reserve(wav_floats * 4));
     CU(d_off.reserve(size_t(n_items + 1) * 16));
@@ -358,15 +368,13 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         for (int i = 0; i < n_items; ++i) {
             Seg& s = segs[i];
             const int64_t plen = 256 * (int64_t(b.n_frames[i]) + 1);
-            s.base = b.padded.as<float>() + size_t(b.pad_offsets[i]) * n_chan;
-            s.chan_stride = int32_t(plen);
-            s.n_rows = b.n_frames[i] + 1;
+            s.base = b.padded.as<float>() + size_t(b.pad_offsets[i]) * n_pairs * 2;
+            s.pair_stride = int32_t(2 * plen);
             s.shift = 0;
             s.t_lo = 0;
             s.t_hi = b.n_frames[i];
             s.gain = 1.f;
             s.keep_idx = -1;
-            s.pad_ = 0;
             ptr[i] = i;
         }
         ptr[n_items] = n_items;
@@ -382,9 +390,7 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         p.seg_ptr = dp;
         p.B = n_items;
         p.T = b.max_frames;
-        p.C = n_chan;
-        p.n_pairs = (n_chan + 1) / 2;
-        p.c_out = n_chan;
+        set_geometry(p, n_chan);
         p.activity = b.activity.as<uint8_t>();
         CU(launch_fused(p, FM_ACTIVITY, c->num_sms, st));
         b.h_activity.resize(act_bytes);
@@ -438,6 +444,8 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     if (M > 0 && (!pl->n_noises || !pl->noise_id || !pl->noise_gain || !pl->noise_offset))
         return fail(IRIS_ERR_INVALID, "noise draws NULL");
     const int C = bg.n_chan;
+    if ((V > 0 && vb.n_chan != C) || (M > 0 && nb.n_chan != C))
+        return fail(IRIS_ERR_INVALID, "all banks must have the same channel count");
     const int n_tm = pl->time_masks ? pl->n_time_masks : 0;
     const int n_fm = pl->freq_masks ? pl->n_freq_masks : 0;
     if (n_tm < 0 || n_tm > 64) return fail(IRIS_ERR_UNSUPPORTED, "more than 64 time masks");
@@ -460,15 +468,13 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         if (lo >= hi) return;
         Seg s;
         const int64_t plen = 256 * (int64_t(bank.n_frames[id]) + 1);
-        s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * bank.n_chan;
-        s.chan_stride = int32_t(plen);
-        s.n_rows = bank.n_frames[id] + 1;
+        s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * ((bank.n_chan + 1) / 2) * 2;
+        s.pair_stride = int32_t(2 * plen);
         s.shift = shift;
         s.t_lo = lo;
         s.t_hi = hi;
         s.gain = gain;
         s.keep_idx = keep_idx;
-        s.pad_ = 0;
         c->h_segs.push_back(s);
         c->h_seg_len.push_back(bank.offsets[id + 1] - bank.offsets[id]);
     };
@@ -557,6 +563,11 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
             }
         }
         c->h_seg_ptr[b + 1] = int32_t(c->h_segs.size());
+        if (c->h_seg_ptr[b + 1] - c->h_seg_ptr[b] > fused_max_segments()) {
+            snprintf(msg, sizeof msg, "clip %d mixes %d segments; the fused kernel takes at most %d", b,
+                     c->h_seg_ptr[b + 1] - c->h_seg_ptr[b], fused_max_segments());
+            return fail(IRIS_ERR_UNSUPPORTED, msg);
+        }
         // mask draws (transforms.py:25-26)
         for (int i = 0; i < n_tm; ++i) {
             const int size = pl->time_masks[(size_t(b) * n_tm + i) * 2];
@@ -654,8 +665,8 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     p.segs = c->d_segs;
     p.seg_ptr = c->d_seg_ptr;
     p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
-    p.B = c->B; p.T = c->T; p.C = c->C;
-    p.n_pairs = (c->C + 1) / 2;
+    p.B = c->B; p.T = c->T;
+    set_geometry(p, c->C);
     p.c_out = c->c_out;
     p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
     p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
@@ -664,19 +675,19 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
     p.out = d_out;
     if (mel) {
-        if (mode == IRIS_FEAT_LOGMEL_MINMAX) {
-            CU(c->minmax.reserve(size_t(c->B) * 8));
-            CU(cudaMemsetAsync(c->minmax.p, 0, size_t(c->B) * 8, st));
+        p.do_log = mode != IRIS_FEAT_MEL;
+        p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
+        if (p.do_minmax) {   // per-clip (~min, max) bit patterns + tiles-done counters
+            CU(c->minmax.reserve(size_t(c->B) * 12));
+            CU(cudaMemsetAsync(c->minmax.p, 0, size_t(c->B) * 12, st));
             p.minmax = c->minmax.as<uint32_t>();
+            p.clip_done = p.minmax + 2 * size_t(c->B);
         }
         rc = timed_fused(c, p, FM_MEL, st);
-        if (rc) return rc;
-        CU(launch_logmel_post(d_out, p.minmax, c->B, size_t(c->n_mel) * c->T * c->C,
-                              mode == IRIS_FEAT_LOGMEL_MINMAX, mode != IRIS_FEAT_MEL, st));
     } else {
         rc = timed_fused(c, p, mode, st);
-        if (rc) return rc;
     }
+    if (rc) return rc;
     return IRIS_OK;
 }
 
@@ -688,16 +699,18 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t kT = 1 + n / kHop, plen = 256 * (kT + 1);
-    CU(c->stft_pad.reserve(size_t(plen + n) * n_chan * 4));
+    if (n_chan > 32) return fail(IRIS_ERR_UNSUPPORTED, "more than 32 channels");
+    const int n_pairs = (n_chan + 1) / 2;
+    CU(c->stft_pad.reserve((size_t(plen) * n_pairs * 2 + size_t(n) * n_chan) * 4));
     CU(c->stft_small.reserve(256));
     float* P = c->stft_pad.as<float>();
-    float* raw = P + size_t(plen) * n_chan;
+    float* raw = P + size_t(plen) * n_pairs * 2;
     CU(cudaMemcpyAsync(raw, wav, size_t(n) * n_chan * 4, cudaMemcpyDefault, st));
     struct Small { int64_t off[2]; int64_t poff[2]; Seg seg; int32_t ptr[2]; } h;
     h.off[0] = 0; h.off[1] = n; h.poff[0] = 0; h.poff[1] = plen;
-    h.seg.base = P; h.seg.chan_stride = int32_t(plen); h.seg.n_rows = int32_t(kT + 1);
+    h.seg.base = P; h.seg.pair_stride = int32_t(2 * plen);
     h.seg.shift = 0; h.seg.t_lo = 0; h.seg.t_hi = int32_t(kT); h.seg.gain = 1.f;
-    h.seg.keep_idx = -1; h.seg.pad_ = 0;
+    h.seg.keep_idx = -1;
     h.ptr[0] = 0; h.ptr[1] = 1;
     CU(cudaMemcpyAsync(c->stft_small.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));   // h is on the stack
@@ -707,9 +720,8 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
     fill_common(c, p);
     p.segs = &d->seg;
     p.seg_ptr = d->ptr;
-    p.B = 1; p.T = int32_t(kT); p.C = n_chan;
-    p.n_pairs = (n_chan + 1) / 2;
-    p.c_out = n_chan;
+    p.B = 1; p.T = int32_t(kT);
+    set_geometry(p, n_chan);
     p.out = d_out;
     CU(launch_fused(p, FM_COMPLEX, c->num_sms, st));
     return IRIS_OK;

@@ -11,20 +11,18 @@ constexpr int kNFft = 512;
 constexpr int kHop = 256;
 constexpr int kBins = 257;
 
-// One mixing segment of one output clip: source frames k = t + shift of the padded
-// waveform P (P[c][i] = reflect-padded, normalised x[c][i-256]; row h = P[256h .. 256h+256))
-// contribute gain * frame_k to output frames t in [t_lo, t_hi).
+// One mixing segment of one output clip: source frames k = t + shift of the padded,
+// pair-interleaved waveform P (k_bank.cu; row h of a pair plane = P[256h .. 256h+256) as
+// float2) contribute gain * frame_k to output frames t in [t_lo, t_hi).
 struct Seg {
-    const float* base;    // channel 0 of P
-    int32_t chan_stride;  // floats between channels of P
-    int32_t n_rows;       // kT + 1 rows of 256 floats per channel
+    const float* base;    // pair plane 0 of P
+    int32_t pair_stride;  // floats between pair planes (= 2 * 256 * (kT + 1))
     int32_t shift;        // k = t + shift
     int32_t t_lo, t_hi;   // valid output frames
     float gain;
     int32_t keep_idx;     // index into keep[] (voice accept flags) or -1
-    int32_t pad_;
 };
-static_assert(sizeof(Seg) == 40, "Seg layout");
+static_assert(sizeof(Seg) == 32, "Seg layout");
 
 enum FusedMode : int {
     FM_COMPLEX = 0,
@@ -42,6 +40,8 @@ struct FusedParams {
     const uint8_t* keep;     // voice accept flags, may be null
     int32_t B, T, C;         // clips, frames per clip, input channels
     int32_t n_pairs;         // ceil(C/2)
+    int32_t np_shift;        // log2(NP): a tile is (16 >> np_shift) frames x NP channel pairs
+    int32_t n_groups;        // ceil(n_pairs / NP)
     int32_t c_out;           // output channels (C unless remapped)
     // SpecAugment rectangles (size, offset) per clip; null => none
     const int32_t* tmask;
@@ -55,16 +55,19 @@ struct FusedParams {
     // outputs
     float* out;             // layout depends on mode
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
-    uint32_t* minmax;       // FM_MEL: [B,2] atomicMax of (~bits, bits); may be null
-    // mel projection (CSR by mel bin, ascending f)
+    // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
+    int32_t do_log, do_minmax;
+    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)), zeroed by the caller
+    uint32_t* clip_done;    // [B] tiles finished per clip, zeroed by the caller
+    // mel projection: filter m covers bins [mel_start[m], +mel_len[m]) with weights at mel_woff[m]
     int32_t n_mel;
     int32_t mel_f_lo;       // lowest bin with a non-zero weight
     int32_t mel_f_n;        // number of bins in [f_lo, f_hi]
-    const int32_t* mel_ptr;  // [n_mel+1]
-    const int16_t* mel_f;    // [nnz]
-    const float* mel_w;      // [nnz]
+    int32_t mel_nw;         // number of stored weights
+    const uint32_t* mel_info;  // [n_mel] start | len << 9 | woff << 18
+    const float* mel_w;        // [mel_nw]
     // tables
-    const float2* tw;       // [32][16] W512^(k1*n2)
+    const float4* tw4;      // [16][16] {W512^(n2*2m), W512^(n2*(2m+1))}
     const float* whalf;     // [512] 0.5 * hann
 };
 
@@ -109,6 +112,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
             "r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

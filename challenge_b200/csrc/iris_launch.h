@@ -8,7 +8,8 @@ namespace iris {
 struct FusedParams;
 
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream);
-int fused_max_mel_window();
+size_t fused_smem_bytes(const FusedParams& p, int mode);
+int fused_max_segments();   // mixing segments one clip may have
 
 // k_post.cu
 cudaError_t launch_logmel_post(float* x, const uint32_t* minmax, int B, size_t per_clip, int do_minmax,

@@ -1,9 +1,12 @@
 // Bank registration = data_utils.load_wav minus decode and STFT (data_utils.py:9-29):
 // RMS-normalise each source over all channels and samples (normalize, 32-34) and lay it
-// out as the reflect-padded waveform P[c][i] = x~[c][i-256], i in [0, 256*(kT+1)), exactly
-// the samples torch.stft(center=True, pad_mode='reflect') frames at hop 256.  Row h of P
-// (256 floats, 1 KB aligned) is both the 2nd half of frame h-1 and the 1st half of frame h,
-// so the hot kernel can fetch any frame range with aligned 1 KB bulk copies.
+// out as the reflect-padded, CHANNEL-PAIR-INTERLEAVED waveform
+//     P[pair][i][c] = x~[2*pair + c][i - 256],   i in [0, 256*(kT+1)),  c in {0,1}
+// (a missing odd channel is zero), exactly the samples torch.stft(center=True,
+// pad_mode='reflect') frames at hop 256.  Row h of a pair plane (256 float2 = 2 KB) is both
+// the 2nd half of frame h-1 and the 1st half of frame h, so the hot kernel fetches any frame
+// range of a source with ONE aligned bulk copy per channel pair, and a lane reads the packed
+// complex FFT input (re = even channel, im = odd channel) with one 64-bit shared load.
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
@@ -40,16 +43,20 @@ __global__ void __launch_bounds__(1024) k_bank_prepare(const float* __restrict__
         __syncthreads();
         scale_div = s_scale;
     }
+    const int n_pairs = (n_chan + 1) >> 1;
     const int64_t kT = 1 + n / kHop;
     const int64_t plen = 256 * (kT + 1);
-    float* P = padded + pad_offsets[item] * n_chan;                // [C, plen]
-    for (int64_t i = threadIdx.x; i < plen * n_chan; i += blockDim.x) {
-        const int64_t c = i / plen, j = i - c * plen;
+    float2* P = reinterpret_cast<float2*>(padded) + pad_offsets[item] * n_pairs;   // [pairs, plen]
+    for (int64_t i = threadIdx.x; i < plen * n_pairs; i += blockDim.x) {
+        const int64_t pr = i / plen, j = i - pr * plen;
         int64_t src = j - 256;
         if (src < 0) src = -src;
         if (src >= n) src = 2 * (n - 1) - src;
-        const float v = x[c * n + src];
-        P[i] = normalize ? v / scale_div : v;
+        const int c0 = int(2 * pr), c1 = c0 + 1;
+        float a = x[c0 * n + src];
+        float b = c1 < n_chan ? x[c1 * n + src] : 0.f;
+        if (normalize) { a = a / scale_div; b = b / scale_div; }
+        P[i] = make_float2(a, b);
     }
 }
 
