@@ -84,6 +84,8 @@ struct iris_ctx {
     std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
     std::vector<int32_t> h_seg_ptr;
     DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
+    DevBuf tiles, sched;
+    int max_segs = 1;
     void* h_stage = nullptr;  // pinned staging for the plan blob
     size_t h_stage_cap = 0;
     cudaEvent_t stage_free = nullptr;
@@ -121,6 +123,8 @@ int build_tables(iris_ctx* c) {
     CU(c->whalf.reserve(wh.size() * 4));
     CU(cudaMemcpy(c->tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->whalf.p, wh.data(), wh.size() * 4, cudaMemcpyHostToDevice));
+    CU(c->sched.reserve(16));
+    CU(cudaMemset(c->sched.p, 0, 16));
     return IRIS_OK;
 }
 
@@ -191,11 +195,21 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
     return IRIS_OK;
 }
 
-int timed_fused(iris_ctx* c, const FusedParams& p, int mode, cudaStream_t st) {
-    if (!c->profile) {
-        CU(launch_fused(p, mode, c->num_sms, st));
-        return IRIS_OK;
-    }
+// tile-block scratch + scheduler words of a launch, then k_tiles + k_fused
+int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
+    p.max_segs = max_segs < 1 ? 1 : max_segs;
+    int stride = 0;
+    const size_t bytes = fused_tile_bytes(p, &stride);
+    CU(c->tiles.reserve(bytes));
+    p.tile_blocks = c->tiles.as<unsigned char>();
+    p.tile_stride = stride;
+    p.sched = c->sched.as<uint32_t>();
+    CU(launch_fused(p, mode, c->num_sms, st));
+    return IRIS_OK;
+}
+
+int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
+    if (!c->profile) return run_fused(c, p, mode, c->max_segs, st);
     if (c->prof_used == c->prof_events.size()) {
         cudaEvent_t a, b;
         CU(cudaEventCreate(&a));
@@ -204,7 +218,8 @@ int timed_fused(iris_ctx* c, const FusedParams& p, int mode, cudaStream_t st) {
     }
     auto& ev = c->prof_events[c->prof_used++];
     CU(cudaEventRecord(ev.first, st));
-    CU(launch_fused(p, mode, c->num_sms, st));
+    int rc = run_fused(c, p, mode, c->max_segs, st);
+    if (rc) return rc;
     CU(cudaEventRecord(ev.second, st));
     return IRIS_OK;
 }
@@ -258,7 +273,7 @@ int iris_ctx_destroy(iris_ctx* c) {
         b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
     }
     for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
-                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small})
+                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->sched})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stage_free) cudaEventDestroy(c->stage_free);
@@ -294,6 +309,10 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
         f_hi = std::max(f_hi, hi);
     }
     if (f_hi < 0) { f_lo = 0; f_hi = 0; }
+    if (f_hi - f_lo + 1 > fused_max_mel_window() || int(fw.size()) > fused_max_mel_weights())
+        return fail(IRIS_ERR_UNSUPPORTED,
+                    "mel matrix spans more than 136 bins or holds more than 512 weights; use the "
+                    "unfused mel projection");
     CU(c->mel_info.reserve(info.size() * 4));
     CU(c->mel_w.reserve(fw.size() * 4 + 4));
     CU(cudaMemcpy(c->mel_info.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice));
@@ -392,7 +411,8 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         p.T = b.max_frames;
         set_geometry(p, n_chan);
         p.activity = b.activity.as<uint8_t>();
-        CU(launch_fused(p, FM_ACTIVITY, c->num_sms, st));
+        rc = run_fused(c, p, FM_ACTIVITY, 1, st);
+        if (rc) return rc;
         b.h_activity.resize(act_bytes);
         CU(cudaMemcpyAsync(b.h_activity.data(), b.activity.p, act_bytes, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -479,6 +499,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         c->h_seg_len.push_back(bank.offsets[id + 1] - bank.offsets[id]);
     };
     char msg[160];
+    int max_segs = 1;
     for (int b = 0; b < B; ++b) {
         // background: tile ceil(T/bgT) times, crop at bg_offset (pipeline.py:29-35)
         const int id = pl->bg_id[b];
@@ -563,6 +584,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
             }
         }
         c->h_seg_ptr[b + 1] = int32_t(c->h_segs.size());
+        max_segs = std::max(max_segs, c->h_seg_ptr[b + 1] - c->h_seg_ptr[b]);
         if (c->h_seg_ptr[b + 1] - c->h_seg_ptr[b] > fused_max_segments()) {
             snprintf(msg, sizeof msg, "clip %d mixes %d segments; the fused kernel takes at most %d", b,
                      c->h_seg_ptr[b + 1] - c->h_seg_ptr[b], fused_max_segments());
@@ -631,6 +653,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     c->filter_k = pl->stft_filter > 0 ? pl->stft_filter : 0;
     c->remap = pl->chan_remap;
     c->c_out = c_out;
+    c->max_segs = max_segs;
     c->has_plan = true;
     c->labels_done = false;
     return IRIS_OK;
@@ -677,9 +700,11 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     if (mel) {
         p.do_log = mode != IRIS_FEAT_MEL;
         p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
-        if (p.do_minmax) {   // per-clip (~min, max) bit patterns + tiles-done counters
+        if (p.do_minmax) {   // per-clip (~min, max) bit patterns + tiles-done counters; the
+                             // kernel leaves them zeroed, so only a fresh allocation is cleared
+            const void* before = c->minmax.p;
             CU(c->minmax.reserve(size_t(c->B) * 12));
-            CU(cudaMemsetAsync(c->minmax.p, 0, size_t(c->B) * 12, st));
+            if (c->minmax.p != before) CU(cudaMemsetAsync(c->minmax.p, 0, c->minmax.cap, st));
             p.minmax = c->minmax.as<uint32_t>();
             p.clip_done = p.minmax + 2 * size_t(c->B);
         }
@@ -723,8 +748,7 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
     p.B = 1; p.T = int32_t(kT);
     set_geometry(p, n_chan);
     p.out = d_out;
-    CU(launch_fused(p, FM_COMPLEX, c->num_sms, st));
-    return IRIS_OK;
+    return run_fused(c, p, FM_COMPLEX, 1, st);
 }
 
 int iris_metric_counts(iris_ctx* c, const float* y_true, const float* y_pred, int B, int T, int K,

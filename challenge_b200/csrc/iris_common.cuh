@@ -52,13 +52,18 @@ struct FusedParams {
     int32_t remap;
     const float* merge_f;   // [B, c_out-2] factor
     const float* merge_sf;  // [B, c_out-2] sqrt(1-factor)
+    // per-tile stage lists (k_tiles -> k_fused) and the dynamic tile scheduler
+    unsigned char* tile_blocks;  // [n_tiles] blocks of tile_stride bytes
+    int32_t tile_stride;
+    int32_t max_segs;            // most mixing segments any clip has
+    uint32_t* sched;             // [2] next tile, CTAs finished; zero between launches
     // outputs
     float* out;             // layout depends on mode
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
     int32_t do_log, do_minmax;
-    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)), zeroed by the caller
-    uint32_t* clip_done;    // [B] tiles finished per clip, zeroed by the caller
+    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); zero between launches
+    uint32_t* clip_done;    // [B] tiles finished per clip; zero between launches
     // mel projection: filter m covers bins [mel_start[m], +mel_len[m]) with weights at mel_woff[m]
     int32_t n_mel;
     int32_t mel_f_lo;       // lowest bin with a non-zero weight

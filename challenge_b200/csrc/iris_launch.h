@@ -9,7 +9,10 @@ struct FusedParams;
 
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
-int fused_max_segments();   // mixing segments one clip may have
+int fused_max_segments();      // mixing segments one clip may have
+int fused_max_mel_window();    // widest bin range [f_lo, f_hi] of the mel matrix
+int fused_max_mel_weights();   // stored mel weights
+size_t fused_tile_bytes(const FusedParams& p, int* stride_out);   // size of p.tile_blocks
 
 // k_post.cu
 cudaError_t launch_logmel_post(float* x, const uint32_t* minmax, int B, size_t per_clip, int do_minmax,

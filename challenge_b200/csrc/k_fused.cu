@@ -1,4 +1,4 @@
-// Fused hot path (v2): gather + time-domain mix of the gained source frames (TMA bulk
+// Fused hot path (v3): gather + time-domain mix of the gained source frames (TMA bulk
 // copies into a 2-slot shared-memory ring), window, 512-point FFT per frame (two real
 // channels packed into one complex transform, one half-warp per FFT), then the epilogue
 // (SpecAugment masks, channel remap, stft_filter, complex / mag-phase / log-mag-phase
@@ -13,13 +13,18 @@
 // using linearity of the STFT: sum_k g_k STFT(src_k)[frame] = FFT(w * sum_k g_k frame_k).
 //
 // Structure.  A tile is FR = 16/NP output frames x NP channel pairs of one clip (NP = 1 for
-// <= 2 channels, 2 for <= 4, ...): 16 half-warp FFT slots, 8 warps, 2 CTAs per SM.  Every
-// mixing segment that overlaps a tile is one STAGE: (FR+1) 2 KB rows per pair, fetched with
-// one cp.async.bulk per pair into slot (stage & 1) and consumed by all 8 warps.  There is no
-// producer warp: the LAST warp to finish reading a slot (shared-memory counter) issues the
-// copy of stage+2 into it, so loads run two stages ahead while the FFTs execute.  Stage lists
-// of the next tiles are compacted by one warp three tiles ahead (keep flags, overlap tests)
-// into a 4-deep ring in shared memory.
+// <= 2 channels, 2 for <= 4, ...): 16 half-warp FFT slots, 8 warps, 2 CTAs per SM.
+//  * k_tiles (one thread per tile) compacts, for every tile, the mixing segments that are
+//    kept and overlap it into a TileBlock (stage descriptors + the tile's mask bits).
+//  * k_fused CTAs claim tiles from a global counter (dynamic scheduling; a CTA that runs a
+//    clip's min-max tail simply claims fewer tiles) and stream the TileBlocks of the next
+//    tiles into a 4-deep shared-memory ring with cp.async, three tiles ahead.
+//  * Every stage of a tile is (FR+1) 2 KB rows per pair, fetched with one cp.async.bulk per
+//    pair into slot (stage & 1) and consumed by all 8 warps.  There is no producer warp: the
+//    LAST warp to finish reading a slot (shared-memory counter) issues the copy of stage+2
+//    into it, so loads run two stages ahead while the FFTs execute.
+//  * LOGMEL_MINMAX: per-tile min/max go to global atomics; the CTA that completes a clip
+//    (per-clip tile counter) normalises and logs the clip in place while it is still in L2.
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
@@ -28,9 +33,11 @@ namespace iris {
 constexpr int kSlots = 16;       // half-warp FFT slots per CTA
 constexpr int kWarps = 8;
 constexpr int kThreads = 256;
-constexpr int kRing = 4;         // tile stage lists in flight
+constexpr int kRing = 4;         // TileBlocks in flight per CTA
 constexpr int kMelPad = 34;      // mel tile row stride in floats (conflict-free float2 columns)
 constexpr int kMaxStages = 32;   // mixing segments of one clip (upper bound on stages per tile)
+constexpr int kMaxMel = 128;
+constexpr int kMaxMelW = 512;
 
 struct StageDesc {
     const float* src;      // first row of pair plane (group * NP) of the source
@@ -41,115 +48,123 @@ struct StageDesc {
 };
 static_assert(sizeof(StageDesc) == 24, "StageDesc layout");
 
-struct TileHdr {
-    int32_t n, b, group, t0;
+struct TileBlock {
+    int32_t n;             // stages (>= 1); 0 = end of work
+    int32_t b;             // clip
+    int32_t t0_group;      // first frame | group << 24
+    uint32_t tmask_bits;   // bit j: frame t0 + j is time-masked (transforms.py:12-40)
+    int16_t fm[8];         // (size, offset) x 4 frequency masks of the clip
+    StageDesc d[kMaxStages];
 };
+static_assert(sizeof(TileBlock) == 32 + 24 * kMaxStages, "TileBlock layout");
+constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
-struct Layout {
-    uint32_t slot_floats, plane_floats, xch_floats;
-    uint32_t off_slots, off_xch, off_mel, off_tw, off_wh, off_minfo, off_mw, off_lists, off_hdr,
-        off_bars, total;
-};
+// ---- shared memory map (bytes) ----
+constexpr int OFF_FULL = 0;      // uint64 full[2]
+constexpr int OFF_CNT = 16;      // int cnt[2]
+constexpr int OFF_CLAIM = 32;    // int claimed[8]
+constexpr int OFF_RING = 128;
+constexpr int OFF_TW = OFF_RING + kRing * kTileBlockBytes;
+constexpr int OFF_WH = OFF_TW + 256 * 16;
+constexpr int OFF_MINFO = OFF_WH + 512 * 4;
+constexpr int OFF_MW = OFF_MINFO + kMaxMel * 4;
+constexpr int OFF_XCH = OFF_MW + kMaxMelW * 4;
+constexpr int OFF_SLOTS = OFF_XCH + kSlots * kXchSlotFloats * 4;
+static_assert(OFF_SLOTS % 128 == 0, "slot alignment");
 
-__host__ __device__ inline Layout make_layout(int np_shift, bool mel, int n_mel, int mel_f_n,
-                                              int mel_nw) {
-    Layout L;
-    const uint32_t NP = 1u << np_shift, FR = 16u >> np_shift;
-    L.plane_floats = (FR + 1) * 512;
-    L.slot_floats = NP * L.plane_floats;
-    L.xch_floats = kXchSlotFloats;
-    if (mel && uint32_t(2 * mel_f_n) > L.xch_floats) L.xch_floats = (2 * mel_f_n + 3) & ~3u;
-    uint32_t o = 0;
-    auto take = [&o](uint32_t bytes) { const uint32_t at = o; o += (bytes + 15u) & ~15u; return at; };
-    L.off_slots = take(2 * L.slot_floats * 4);
-    L.off_xch = take(kSlots * L.xch_floats * 4);
-    L.off_mel = take(mel ? uint32_t(n_mel) * kMelPad * 4 : 0);
-    L.off_tw = take(256 * 16);
-    L.off_wh = take(512 * 4);
-    L.off_minfo = take(mel ? uint32_t(n_mel) * 4 : 0);
-    L.off_mw = take(mel ? uint32_t(mel_nw) * 4 : 0);
-    L.off_lists = take(kRing * kMaxStages * uint32_t(sizeof(StageDesc)));
-    L.off_hdr = take(kRing * uint32_t(sizeof(TileHdr)));
-    L.off_bars = take(64);
-    L.total = o;
-    return L;
+__host__ __device__ inline uint32_t slot_bytes(int np_shift) {
+    return (1u << np_shift) * ((16u >> np_shift) + 1u) * 2048u;
+}
+__host__ __device__ inline uint32_t smem_total(int np_shift, bool mel, int n_mel) {
+    return OFF_SLOTS + 2 * slot_bytes(np_shift) + (mel ? uint32_t(n_mel) * kMelPad * 4 : 0);
 }
 
-struct TileGeom {
-    int FR, tpc, per_clip, n_tiles;
-};
-__device__ __forceinline__ TileGeom tile_geom(const FusedParams& p) {
-    TileGeom g;
-    g.FR = 16 >> p.np_shift;
-    g.tpc = (p.T + g.FR - 1) / g.FR;
-    g.per_clip = g.tpc * p.n_groups;
-    g.n_tiles = p.B * g.per_clip;
-    return g;
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-// One warp compacts the stages of `tile` (mixing segments that are kept and overlap it).
-__device__ __forceinline__ void build_list(const FusedParams& p, const TileGeom& g, int tile,
-                                           TileHdr* hdr, StageDesc* list, int lane) {
-    const int b = tile / g.per_clip;
-    const int r = tile - b * g.per_clip;
-    const int group = r / g.tpc;
-    const int t0 = (r - group * g.tpc) * g.FR;
-    const int t_end = min(t0 + g.FR, p.T);
-    const int s1 = p.seg_ptr[b + 1];
+// ---- pre-kernel: one thread per tile builds its TileBlock ----
+__global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
+    const int FR = 16 >> p.np_shift;
+    const int tpc = (p.T + FR - 1) / FR;
+    const int per_clip = tpc * p.n_groups;
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= p.B * per_clip) return;
+    const int b = tile / per_clip;
+    const int r = tile - b * per_clip;
+    const int group = r / tpc;
+    const int t0 = (r - group * tpc) * FR;
+    const int t_end = min(t0 + FR, p.T);
+    unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
+    StageDesc* d = reinterpret_cast<StageDesc*>(blk + 32);
     int n = 0;
-    for (int base = p.seg_ptr[b]; base < s1; base += 32) {
-        const int s = base + lane;
-        bool valid = false;
-        Seg sg;
-        int lo = 0, hi = 0;
-        if (s < s1) {
-            sg = p.segs[s];
-            lo = max(sg.t_lo, t0);
-            hi = min(sg.t_hi, t_end);
-            valid = lo < hi && !(sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0);
+    const int s1 = p.seg_ptr[b + 1];
+    for (int s = p.seg_ptr[b]; s < s1; ++s) {
+        const Seg sg = p.segs[s];
+        const int lo = max(sg.t_lo, t0), hi = min(sg.t_hi, t_end);
+        if (lo >= hi || (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0)) continue;
+        if (n < p.max_segs) {
+            StageDesc e;
+            e.src = sg.base + size_t(group << p.np_shift) * size_t(sg.pair_stride) +
+                    size_t(lo + sg.shift) * 512;
+            e.pair_stride = uint32_t(sg.pair_stride);
+            e.j_lo = uint16_t(lo - t0);
+            e.j_cnt = uint16_t(hi - lo);
+            e.gain = sg.gain;
+            e.pad_ = 0;
+            d[n++] = e;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const int pos = n + __popc(bal & ((1u << lane) - 1u));
-            if (pos < kMaxStages) {
-                StageDesc d;
-                d.src = sg.base + size_t(group << p.np_shift) * size_t(sg.pair_stride) +
-                        size_t(lo + sg.shift) * 512;
-                d.pair_stride = uint32_t(sg.pair_stride);
-                d.j_lo = uint16_t(lo - t0);
-                d.j_cnt = uint16_t(hi - lo);
-                d.gain = sg.gain;
-                d.pad_ = 0;
-                list[pos] = d;
-            }
-        }
-        n += __popc(bal);
     }
-    if (lane == 0) {
-        if (n == 0) {   // nothing overlaps: one empty stage keeps the ring protocol uniform
-            StageDesc d;
-            d.src = nullptr; d.pair_stride = 0; d.j_lo = 0; d.j_cnt = 0; d.gain = 0.f; d.pad_ = 0;
-            list[0] = d;
-            n = 1;
-        }
-        TileHdr h;
-        h.n = min(n, kMaxStages); h.b = b; h.group = group; h.t0 = t0;
-        *hdr = h;
+    if (n == 0) {   // nothing overlaps: one empty stage keeps the ring protocol uniform
+        StageDesc e;
+        e.src = nullptr; e.pair_stride = 0; e.j_lo = 0; e.j_cnt = 0; e.gain = 0.f; e.pad_ = 0;
+        d[n++] = e;
     }
-    __syncwarp();
+    uint32_t tbits = 0;
+    if (p.tmask != nullptr) {
+        const int32_t* tm = p.tmask + size_t(b) * p.n_tmask * 2;
+        for (int i = 0; i < p.n_tmask; ++i) {
+            const int size = tm[2 * i], off = tm[2 * i + 1];
+            const int lo = max(off, t0), hi = min(off + size, t_end);
+            if (lo < hi) tbits |= ((1u << (hi - lo)) - 1u) << (lo - t0);
+        }
+    }
+    int4 hdr;
+    hdr.x = n; hdr.y = b; hdr.z = t0 | (group << 24); hdr.w = int(tbits);
+    *reinterpret_cast<int4*>(blk) = hdr;
+    int16_t fm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fm[i] = 0;
+    if (p.fmask != nullptr) {
+        const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
+        for (int i = 0; i < p.n_fmask && i < 4; ++i) {
+            fm[2 * i] = int16_t(fk[2 * i]);
+            fm[2 * i + 1] = int16_t(fk[2 * i + 1]);
+        }
+    }
+    *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
 }
 
-__device__ __forceinline__ void issue_stage(const StageDesc& d, float* slot, uint64_t* full,
-                                            int np_here, uint32_t plane_floats) {
+__device__ __forceinline__ void issue_stage(const StageDesc* dp, uint32_t slot_addr, uint32_t full_addr,
+                                            int np_here, uint32_t plane_bytes) {
+    const StageDesc d = *dp;
     if (d.j_cnt == 0) {
-        mbar_arrive(full);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_addr) : "memory");
         return;
     }
     const uint32_t bytes = (uint32_t(d.j_cnt) + 1u) * 2048u;
-    mbar_arrive_expect_tx(full, bytes * uint32_t(np_here));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_addr),
+                 "r"(bytes * uint32_t(np_here))
+                 : "memory");
     for (int pr = 0; pr < np_here; ++pr)
-        bulk_g2s(slot + pr * plane_floats + uint32_t(d.j_lo) * 512u,
-                 d.src + size_t(pr) * d.pair_stride, bytes, full);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(slot_addr + pr * plane_bytes + uint32_t(d.j_lo) * 2048u),
+            "l"(d.src + size_t(pr) * d.pair_stride), "r"(bytes), "r"(full_addr)
+            : "memory");
 }
 
 template <int MODE>
@@ -215,30 +230,91 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
     }
 }
 
+// min-max + log of one finished clip, in place (data_utils.py:37-55), by the whole CTA:
+// (x - min) / max(max - min, 1e-8), then log(x + 1e-8).  Reads bypass L1 (other CTAs wrote).
+__device__ __noinline__ void clip_tail(const FusedParams& p, int b) {
+    const int tid = threadIdx.x;
+    const float lo = __uint_as_float(~__ldcg(&p.minmax[2 * b]));
+    const float hi = __uint_as_float(__ldcg(&p.minmax[2 * b + 1]));
+    const float den = fmaxf(hi - lo, 1e-8f);
+    const size_t per = size_t(p.n_mel) * p.T * p.C;
+    float* base = p.out + size_t(b) * per;
+    const bool lg = p.do_log != 0;
+    if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        float4* v4 = reinterpret_cast<float4*>(base);
+        const int n4 = int(per >> 2);
+        for (int i = tid; i < n4; i += 4 * kThreads) {
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * kThreads < n4) a[u] = __ldcg(v4 + i + u * kThreads);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + u * kThreads < n4) {
+                    a[u].x = __fdividef(a[u].x - lo, den);
+                    a[u].y = __fdividef(a[u].y - lo, den);
+                    a[u].z = __fdividef(a[u].z - lo, den);
+                    a[u].w = __fdividef(a[u].w - lo, den);
+                    if (lg) {
+                        a[u].x = __logf(a[u].x + 1e-8f);
+                        a[u].y = __logf(a[u].y + 1e-8f);
+                        a[u].z = __logf(a[u].z + 1e-8f);
+                        a[u].w = __logf(a[u].w + 1e-8f);
+                    }
+                    v4[i + u * kThreads] = a[u];
+                }
+            }
+        }
+    } else {
+        for (size_t i = tid; i < per; i += kThreads) {
+            float a = __fdividef(__ldcg(base + i) - lo, den);
+            base[i] = lg ? __logf(a + 1e-8f) : a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {   // leave the per-clip scratch zeroed for the next launch
+        p.minmax[2 * b] = 0u;
+        p.minmax[2 * b + 1] = 0u;
+        p.clip_done[b] = 0u;
+    }
+}
+
 // KB: number of 32-bin groups the epilogue needs (mel support below bin 32*KB); 8 = all bins.
 template <int MODE, int KB>
 __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ FusedParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char sm[];
     constexpr bool kMel = (MODE == FM_MEL);
-    const Layout L = make_layout(p.np_shift, kMel, p.n_mel, p.mel_f_n, p.mel_nw);
-    float* slots = reinterpret_cast<float*>(smem_raw + L.off_slots);
-    float* xch = reinterpret_cast<float*>(smem_raw + L.off_xch);
-    float* meltile = reinterpret_cast<float*>(smem_raw + L.off_mel);
-    float4* s_tw4 = reinterpret_cast<float4*>(smem_raw + L.off_tw);
-    float* s_wh = reinterpret_cast<float*>(smem_raw + L.off_wh);
-    uint32_t* s_minfo = reinterpret_cast<uint32_t*>(smem_raw + L.off_minfo);
-    float* s_mw = reinterpret_cast<float*>(smem_raw + L.off_mw);
-    StageDesc* lists = reinterpret_cast<StageDesc*>(smem_raw + L.off_lists);
-    TileHdr* hdrs = reinterpret_cast<TileHdr*>(smem_raw + L.off_hdr);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bars);   // [2]
-    int* cnt = reinterpret_cast<int*>(full + 2);                           // [2]
-    int* s_flag = cnt + 2;
-
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, hw = lane >> 4, n2 = lane & 15;
-    const TileGeom g = tile_geom(p);
-    const int n_my = (g.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    const int warp = tid >> 5, lane = tid & 31, n2 = lane & 15;
+    const uint32_t sm_base = smem_u32(sm);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
+    int* cnt = reinterpret_cast<int*>(sm + OFF_CNT);
+    int* claimed = reinterpret_cast<int*>(sm + OFF_CLAIM);
+    float4* s_tw4 = reinterpret_cast<float4*>(sm + OFF_TW);
+    float* s_wh = reinterpret_cast<float*>(sm + OFF_WH);
+    uint32_t* s_minfo = reinterpret_cast<uint32_t*>(sm + OFF_MINFO);
+    float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
+    auto ring = [&](int k) -> TileBlock* {
+        return reinterpret_cast<TileBlock*>(sm + OFF_RING + (k & (kRing - 1)) * kTileBlockBytes);
+    };
     const int NP = 1 << p.np_shift;
+    const int FR = 16 >> p.np_shift;
+    const int per_clip = ((p.T + FR - 1) / FR) * p.n_groups;
+    const int n_tiles = p.B * per_clip;
+    const uint32_t slotB = slot_bytes(p.np_shift);
+    const uint32_t planeB = uint32_t(FR + 1) * 2048u;
+
+    // one warp streams the TileBlock of `tile` into ring entry k (or writes the end marker)
+    auto fetch_block = [&](int k, int tile) {
+        TileBlock* dst = ring(k);
+        if (tile < n_tiles) {
+            const unsigned char* src = p.tile_blocks + size_t(tile) * p.tile_stride;
+            const uint32_t d0 = smem_u32(dst);
+            for (int c = lane * 16; c < p.tile_stride; c += 32 * 16) cp_async16(d0 + c, src + c);
+        } else if (lane == 0) {
+            dst->n = 0;
+        }
+    };
 
     for (int i = tid; i < 256; i += kThreads) s_tw4[i] = p.tw4[i];
     for (int i = tid; i < 512; i += kThreads) s_wh[i] = p.whalf[i];
@@ -251,69 +327,76 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
         mbar_init(&full[1], 1);
         cnt[0] = 0;
         cnt[1] = 0;
-        *s_flag = 0;
         fence_mbar_init();
+        // the first four tiles of this CTA, in order (an end marker must never precede work)
+        const int c = int(atomicAdd(&p.sched[0], 4u));
+        for (int i = 0; i < 4; ++i) claimed[i] = c + i;
     }
-    if (warp < 3 && warp < n_my)
-        build_list(p, g, int(blockIdx.x) + warp * int(gridDim.x), &hdrs[warp],
-                   lists + warp * kMaxStages, lane);
+    __syncthreads();
+    if (warp < 3) {
+        fetch_block(warp, claimed[warp]);
+        cp_async_wait_all();
+    }
     __syncthreads();
 
     // issue cursor = position (tile iteration ki, entry ei) of stage q + 2
     int ki = 0, ei = 0;
     auto advance = [&]() {
-        if (ki < n_my) {
-            if (++ei >= hdrs[ki & (kRing - 1)].n) { ++ki; ei = 0; }
-        }
+        const int n = ring(ki)->n;
+        if (n != 0 && ++ei >= n) { ++ki; ei = 0; }
     };
-    auto np_of = [&](int k) { return min(NP, p.n_pairs - (hdrs[k & (kRing - 1)].group << p.np_shift)); };
+    auto np_of = [&](int k) { return min(NP, p.n_pairs - ((ring(k)->t0_group >> 24) << p.np_shift)); };
     if (tid == 0) {
         int a = 0, e = 0;
-        for (int s = 0; s < 2 && a < n_my; ++s) {
-            issue_stage(lists[(a & (kRing - 1)) * kMaxStages + e], slots + s * L.slot_floats,
-                        &full[s], np_of(a), L.plane_floats);
-            if (++e >= hdrs[a & (kRing - 1)].n) { ++a; e = 0; }
+        for (int s = 0; s < 2; ++s) {
+            const TileBlock* tb = ring(a);
+            if (tb->n == 0) break;
+            issue_stage(&tb->d[e], sm_base + OFF_SLOTS + s * slotB, sm_base + OFF_FULL + 8 * s, np_of(a), planeB);
+            if (++e >= tb->n) { ++a; e = 0; }
         }
     }
     advance();
     advance();
 
-    const int slot = warp * 2 + hw;
-    const unsigned hmask = hw ? 0xFFFF0000u : 0x0000FFFFu;
-    float* xs = xch + slot * L.xch_floats;
+    const int slot = warp * 2 + (lane >> 4);
+    const unsigned hmask = (lane >> 4) ? 0xFFFF0000u : 0x0000FFFFu;
+    float* xs = reinterpret_cast<float*>(sm + OFF_XCH) + slot * kXchSlotFloats;
     const int ka = n2, kb = (n2 == 0) ? 16 : 32 - n2;
     const bool l0 = (n2 == 0);
     const int j = slot >> p.np_shift;          // tile-relative frame of this slot
     const int pr = slot & (NP - 1);            // pair within the tile's group
-    const float2* my_rows = reinterpret_cast<const float2*>(slots + pr * L.plane_floats) + j * 256 + n2;
-    const int slot_f2 = int(L.slot_floats >> 1);
+    const float2* my_rows = reinterpret_cast<const float2*>(sm + OFF_SLOTS + pr * planeB) + j * 256 + n2;
+    float* meltile = reinterpret_cast<float*>(sm + OFF_SLOTS + 2 * slotB);
 
-    int q = 0;   // stages consumed so far
-    for (int k = 0; k < n_my; ++k) {
-        if (warp == (k & (kWarps - 1)) && k + 3 < n_my)
-            build_list(p, g, int(blockIdx.x) + (k + 3) * int(gridDim.x), &hdrs[(k + 3) & (kRing - 1)],
-                       lists + ((k + 3) & (kRing - 1)) * kMaxStages, lane);
-        const TileHdr h = hdrs[k & (kRing - 1)];
-        const StageDesc* list = lists + (k & (kRing - 1)) * kMaxStages;
-        const int b = h.b;
-        const int t = h.t0 + j;
-        const int pair = (h.group << p.np_shift) + pr;
-        const bool pair_ok = pair < p.n_pairs;
-        const bool in_range = t < p.T && pair_ok;
-        const bool has1 = (2 * pair + 1 < p.C);
+    int q = 0;          // stages consumed so far
+    int pend = 0;       // thread 0: this CTA completed clip b_prev (min-max tail pending)
+    int b_prev = 0;
+    for (int k = 0;; ++k) {
+        const TileBlock* tb = ring(k);
+        const int n_st = tb->n;
+        if (n_st == 0) break;
+        int new_claim = 0;
+        const bool builder = warp == (k & (kWarps - 1));
+        if (builder) {   // stream the block of tile k+3, claim the tile of iteration k+4
+            fetch_block(k + 3, claimed[(k + 3) & 7]);
+            if (lane == 0) new_claim = int(atomicAdd(&p.sched[0], 1u));
+        }
 
         float re[32], im[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
 
         // ---- gather + mix: acc += gain * frame_k of every stage of this tile ----
-        for (int e = 0; e < h.n; ++e) {
-            const StageDesc d = list[e];
+        const int group = tb->t0_group >> 24;
+        const bool pair_ok = (group << p.np_shift) + pr < p.n_pairs;
+        for (int e = 0; e < n_st; ++e) {
             const int s = q & 1;
+            const uint32_t jj = *reinterpret_cast<const uint32_t*>(&tb->d[e].j_lo);   // j_lo | j_cnt << 16
+            const float gn = tb->d[e].gain;
             mbar_wait(&full[s], uint32_t(q >> 1) & 1u);
-            if (pair_ok && j >= int(d.j_lo) && j < int(d.j_lo) + int(d.j_cnt)) {
-                const float gn = d.gain;
-                const float2* src = my_rows + s * slot_f2;
+            if (pair_ok && unsigned(j - int(jj & 0xffffu)) < (jj >> 16)) {
+                const float2* src = reinterpret_cast<const float2*>(
+                    reinterpret_cast<const unsigned char*>(my_rows) + s * slotB);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float2 x = src[16 * i];
@@ -326,10 +409,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 const int old = atomicAdd(&cnt[s], 1);
                 if (old == kWarps - 1) {          // last reader of the slot: refill it
                     cnt[s] = 0;
-                    if (ki < n_my) {
+                    const TileBlock* nb = ring(ki);
+                    if (nb->n != 0) {
                         fence_proxy_async();
-                        issue_stage(lists[(ki & (kRing - 1)) * kMaxStages + ei],
-                                    slots + s * L.slot_floats, &full[s], np_of(ki), L.plane_floats);
+                        issue_stage(&nb->d[ei], sm_base + OFF_SLOTS + s * slotB, sm_base + OFF_FULL + 8 * s,
+                                    np_of(ki), planeB);
                     }
                 }
             }
@@ -337,21 +421,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
             advance();
         }
 
-        // ---- SpecAugment time mask of this frame (transforms.py:12-40) ----
-        float mt = 1.f;
-        if (p.tmask != nullptr) {
-            const int32_t* tm = p.tmask + size_t(b) * p.n_tmask * 2;
-            bool hit = false;
-            for (int i0 = 0; i0 < p.n_tmask; i0 += 16) {
-                const int i = i0 + n2;
-                if (i < p.n_tmask) {
-                    const int2 so = *reinterpret_cast<const int2*>(tm + 2 * i);
-                    hit = hit || (t >= so.y && t < so.y + so.x);
-                }
-            }
-            if (__ballot_sync(hmask, hit) & hmask) mt = 0.f;
-        }
-
+        const int b = tb->b;
+        const int t0 = tb->t0_group & 0xffffff;
+        const int t = t0 + j;
+        const int pair = (group << p.np_shift) + pr;
+        const bool in_range = t < p.T && pair_ok;
+        const bool has1 = (2 * pair + 1 < p.C);
+        // SpecAugment time mask of this frame (transforms.py:12-40), precomputed per tile
+        const float mt = ((tb->tmask_bits >> j) & 1u) ? 0.f : 1.f;
         // a fully time-masked frame has zero magnitude everywhere: no FFT needed for mel
         const bool do_fft = in_range && !(kMel && mt == 0.f);
 
@@ -383,17 +460,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 if (rho < 2) {
                     if ((ka >> 3) == rho) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(ka & 7, jj));
-                            Za[jj] = cpx{z.x, z.y};
+                        for (int jx = 0; jx < 16; ++jx) {
+                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(ka & 7, jx));
+                            Za[jx] = cpx{z.x, z.y};
                         }
                     }
                 } else {
                     if ((kb >> 3) == rho) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(kb & 7, jj));
-                            Zb[jj] = cpx{z.x, z.y};
+                        for (int jx = 0; jx < 16; ++jx) {
+                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(kb & 7, jx));
+                            Zb[jx] = cpx{z.x, z.y};
                         }
                     }
                 }
@@ -411,7 +488,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
             float2* mg = reinterpret_cast<float2*>(xs);   // [mel_f_n] (|ch0|, |ch1|), aliases the exchange slot
             const int f_lo = p.mel_f_lo, f_n = p.mel_f_n;
             float acc0[8], acc1[8];   // mel bins m = n2 + 16 r
-            const int n_r = (p.n_mel + 15) >> 4;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
             if (do_fft) {
                 auto emit = [&](int f, cpx zf, cpx zm) {
                     const unsigned fi = unsigned(f - f_lo);
@@ -433,12 +511,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 __syncwarp(hmask);
                 // frequency masks (transforms.py:12-40) and stft_filter (data_utils.py:126-136)
                 // zero whole bins: |x| * 0 == +0
-                if (p.fmask != nullptr || p.filter_k > 0) {
-                    const int32_t* fmk = p.fmask + size_t(b) * p.n_fmask * 2;
-                    const int n_z = (p.fmask != nullptr ? p.n_fmask : 0) + (p.filter_k > 0 ? 1 : 0);
-                    for (int i = 0; i < n_z; ++i) {
+                if (p.n_fmask > 0 || p.filter_k > 0) {
+                    for (int i = 0; i <= p.n_fmask; ++i) {
                         int off, size;
-                        if (p.fmask != nullptr && i < p.n_fmask) { size = fmk[2 * i]; off = fmk[2 * i + 1]; }
+                        if (i < p.n_fmask) { size = tb->fm[2 * i]; off = tb->fm[2 * i + 1]; }
                         else { off = 1; size = p.filter_k; }
                         for (int f = off + n2; f < off + size; f += 16) {
                             const unsigned fi = unsigned(f - f_lo);
@@ -447,24 +523,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                     }
                     __syncwarp(hmask);
                 }
+                const int n_r = (p.n_mel + 15) >> 4;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    acc0[r] = 0.f; acc1[r] = 0.f;
                     const int m = n2 + 16 * r;
                     if (r < n_r && m < p.n_mel) {
                         const uint32_t info = s_minfo[m];
-                        const int start = int(info & 511u) - f_lo, len = int((info >> 9) & 511u);
+                        const float2* a = mg + (int(info & 511u) - f_lo);
+                        const int len = int((info >> 9) & 511u);
                         const float* w = s_mw + (info >> 18);
                         for (int i = 0; i < len; ++i) {
-                            const float2 a = mg[start + i];
-                            acc0[r] = fmaf(w[i], a.x, acc0[r]);
-                            acc1[r] = fmaf(w[i], a.y, acc1[r]);
+                            const float2 x = a[i];
+                            acc0[r] = fmaf(w[i], x.x, acc0[r]);
+                            acc1[r] = fmaf(w[i], x.y, acc1[r]);
                         }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
             }
             __syncwarp();
             // ---- tile of mel values [n_mel][FR frames x C channels] in shared memory ----
@@ -474,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int m = n2 + 16 * r;
-                    if (r < n_r && m < p.n_mel) {
+                    if (m < p.n_mel) {
                         if ((C & 1) == 0) {
                             *reinterpret_cast<float2*>(meltile + m * kMelPad + col) = make_float2(acc0[r], acc1[r]);
                         } else {
@@ -484,12 +558,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                     }
                 }
             }
-            __syncthreads();   // tile complete (also publishes the stage list built this iteration)
+            if (builder) {
+                cp_async_wait_all();
+                if (lane == 0) claimed[(k + 4) & 7] = new_claim;
+            }
+            // tile complete (also publishes the builder's ring entry); with min-max, learn
+            // whether this CTA completed the previous tile's clip
+            int tail = 0;
+            if (p.do_minmax) tail = __syncthreads_or(pend);
+            else __syncthreads();
+            if (tail) clip_tail(p, b_prev);
             // coalesced store [B, n_mel, T, C] (+ log) and per-clip min/max (data_utils.py:37-55)
-            const int fr_valid = min(g.FR, p.T - h.t0);
-            const int ncols = fr_valid * C;
+            const int ncols = min(FR, p.T - t0) * C;
             float mn = __int_as_float(0x7f800000), mx = 0.f;
-            float* orow = p.out + (size_t(b) * p.n_mel * p.T + h.t0) * C;
+            float* orow = p.out + (size_t(b) * p.n_mel * p.T + t0) * C;
+            const bool lg = p.do_log && !p.do_minmax;
             if ((C & 1) == 0) {
                 const int c2 = tid & 15;
                 if (2 * c2 < ncols) {
@@ -497,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                         float2 vv = *reinterpret_cast<const float2*>(meltile + m * kMelPad + 2 * c2);
                         mn = fminf(mn, fminf(vv.x, vv.y));
                         mx = fmaxf(mx, fmaxf(vv.x, vv.y));
-                        if (p.do_log && !p.do_minmax) {
+                        if (lg) {
                             vv.x = __logf(vv.x + 1e-8f);
                             vv.y = __logf(vv.y + 1e-8f);
                         }
@@ -511,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                         float vv = meltile[m * kMelPad + c1];
                         mn = fminf(mn, vv);
                         mx = fmaxf(mx, vv);
-                        if (p.do_log && !p.do_minmax) vv = __logf(vv + 1e-8f);
+                        if (lg) vv = __logf(vv + 1e-8f);
                         orow[size_t(m) * p.T * C + c1] = vv;
                     }
                 }
@@ -526,60 +609,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                     atomicMax(&p.minmax[2 * b], ~__float_as_uint(mn));
                     atomicMax(&p.minmax[2 * b + 1], __float_as_uint(mx));
                 }
-                __threadfence();
             }
-            __syncthreads();   // store phase over: the mel tile may be overwritten
+            __syncthreads();   // store phase over: the mel tile and ring entry k may be reused
             if (p.do_minmax) {
-                // the CTA that completes a clip normalises it in place while it is still in L2:
-                // (x - min) / max(max - min, 1e-8), then log(x + 1e-8)   (data_utils.py:37-55)
                 if (tid == 0) {
-                    const unsigned old = atomicAdd(&p.clip_done[b], 1u);
-                    *s_flag = (old == unsigned(g.per_clip) - 1u) ? 1 : 0;
                     __threadfence();
+                    const unsigned old = atomicAdd(&p.clip_done[b], 1u);
+                    pend = (old == unsigned(per_clip) - 1u) ? 1 : 0;
+                    if (pend) __threadfence();
                 }
-                __syncthreads();
-                if (*s_flag) {
-                    const float lo = __uint_as_float(~__ldcg(&p.minmax[2 * b]));
-                    const float hi = __uint_as_float(__ldcg(&p.minmax[2 * b + 1]));
-                    const float den = fmaxf(hi - lo, 1e-8f);
-                    const size_t per = size_t(p.n_mel) * p.T * C;
-                    float* base = p.out + size_t(b) * per;
-                    if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-                        float4* v4 = reinterpret_cast<float4*>(base);
-                        const int n4 = int(per >> 2);
-                        for (int i = tid; i < n4; i += 4 * kThreads) {
-                            float4 a[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (i + u * kThreads < n4) a[u] = __ldcg(v4 + i + u * kThreads);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (i + u * kThreads < n4) {
-                                    a[u].x = __fdividef(a[u].x - lo, den);
-                                    a[u].y = __fdividef(a[u].y - lo, den);
-                                    a[u].z = __fdividef(a[u].z - lo, den);
-                                    a[u].w = __fdividef(a[u].w - lo, den);
-                                    if (p.do_log) {
-                                        a[u].x = __logf(a[u].x + 1e-8f);
-                                        a[u].y = __logf(a[u].y + 1e-8f);
-                                        a[u].z = __logf(a[u].z + 1e-8f);
-                                        a[u].w = __logf(a[u].w + 1e-8f);
-                                    }
-                                    v4[i + u * kThreads] = a[u];
-                                }
-                            }
-                        }
-                    } else {
-                        for (size_t i = tid; i < per; i += kThreads) {
-                            float a = __ldcg(base + i);
-                            a = __fdividef(a - lo, den);
-                            base[i] = p.do_log ? __logf(a + 1e-8f) : a;
-                        }
-                    }
-                }
+                b_prev = b;
             }
         } else {
-            __syncthreads();   // publishes the stage list built this iteration
             if (MODE == FM_ACTIVITY) {
                 // frame "active" iff any STFT coefficient (any bin, re or im, any channel) > 0
                 // (pipeline.py:55)
@@ -602,21 +643,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 for (int o = 8; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(hmask, mxv, o));
                 if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
             } else if (do_fft) {
-                // per-lane bitmap of frequency-masked / filtered bins: bit k2 -> ka + 32*k2,
+                // per-lane bitmap of frequency-masked bins: bit k2 -> ka + 32*k2,
                 // bit 8 + k2 -> kb + 32*k2, bit 16 -> bin 256
                 uint32_t zbits = 0;
-                {
-                    const int n_z = p.fmask != nullptr ? p.n_fmask : 0;
-                    const int32_t* fmk = p.fmask + size_t(b) * p.n_fmask * 2;
-                    for (int i = 0; i < n_z; ++i) {
-                        const int size = fmk[2 * i], off = fmk[2 * i + 1];
+                for (int i = 0; i < p.n_fmask; ++i) {
+                    const int size = tb->fm[2 * i], off = tb->fm[2 * i + 1];
 #pragma unroll
-                        for (int k2 = 0; k2 < 8; ++k2) {
-                            if (unsigned(ka + 32 * k2 - off) < unsigned(size)) zbits |= 1u << k2;
-                            if (unsigned(kb + 32 * k2 - off) < unsigned(size)) zbits |= 1u << (8 + k2);
-                        }
-                        if (unsigned(256 - off) < unsigned(size)) zbits |= 1u << 16;
+                    for (int k2 = 0; k2 < 8; ++k2) {
+                        if (unsigned(ka + 32 * k2 - off) < unsigned(size)) zbits |= 1u << k2;
+                        if (unsigned(kb + 32 * k2 - off) < unsigned(size)) zbits |= 1u << (8 + k2);
                     }
+                    if (unsigned(256 - off) < unsigned(size)) zbits |= 1u << 16;
                 }
 #pragma unroll
                 for (int k2 = 0; k2 < 8; ++k2) {
@@ -641,24 +678,51 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                                     zf.y + zf.y, zf.x - zf.x, ((zbits >> 16) & 1u) ? 0.f : mt);
                 }
             }
+            if (builder) {
+                cp_async_wait_all();
+                if (lane == 0) claimed[(k + 4) & 7] = new_claim;
+            }
+            __syncthreads();   // ring entry k may be reused; publishes the builder's ring entry
+        }
+    }
+    if (kMel && p.do_minmax) {
+        if (__syncthreads_or(pend)) clip_tail(p, b_prev);
+    }
+    // the last CTA to leave resets the tile scheduler for the next launch
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+            p.sched[0] = 0u;
+            p.sched[1] = 0u;
         }
     }
 }
 
 size_t fused_smem_bytes(const FusedParams& p, int mode) {
-    return make_layout(p.np_shift, mode == FM_MEL, p.n_mel, p.mel_f_n, p.mel_nw).total;
+    return smem_total(p.np_shift, mode == FM_MEL, p.n_mel);
+}
+int fused_max_segments() { return kMaxStages; }
+int fused_max_mel_window() { return kXchSlotFloats / 2; }
+int fused_max_mel_weights() { return kMaxMelW; }
+size_t fused_tile_bytes(const FusedParams& p, int* stride_out) {
+    const int FR = 16 >> p.np_shift;
+    const long long n_tiles = (long long)p.B * p.n_groups * ((p.T + FR - 1) / FR);
+    int ms = p.max_segs < 1 ? 1 : p.max_segs;
+    const int stride = (32 + 24 * ms + 15) & ~15;
+    if (stride_out) *stride_out = stride;
+    return size_t(n_tiles) * size_t(stride);
 }
 
-int fused_max_segments() { return kMaxStages; }
-
+// p.tile_blocks (fused_tile_bytes) and p.sched (2 x uint32, zero) are provided by the caller.
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream) {
     const int FR = 16 >> p.np_shift;
     const int tpc = (p.T + FR - 1) / FR;
     const long long n_tiles = (long long)p.B * p.n_groups * tpc;
     if (n_tiles <= 0) return cudaSuccess;
-    if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (n_tiles > 0x7fffffffLL || p.max_segs > kMaxStages) return cudaErrorInvalidValue;
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
     const int grid = int(n_tiles < 2LL * num_sms ? n_tiles : 2LL * num_sms);
 #define IRIS_LAUNCH(M, KBV)                                                                     \
     {                                                                                           \

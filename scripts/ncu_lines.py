@@ -36,3 +36,8 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 print('--- top lines by instructions')
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print('%5.1f%% ins %5.1f%% smp  %s:%s  %s' % (100*a[1]/tot_i, 100*a[0]/tot_s, k[0], k[1], src_text.get(k, '')[:90]))
+tot = collections.Counter()
+for a in agg.values():
+    tot.update(a[3])
+s = sum(tot.values()) or 1
+print('--- stall reasons overall:', ' '.join('%s:%.1f%%' % (k, 100 * v / s) for k, v in tot.most_common(12)))
