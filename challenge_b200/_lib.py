@@ -7,7 +7,7 @@ import os
 from .errors import InvalidArgumentError, IrisError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libiris.so')
+LIB_PATH = os.environ.get('IRIS_LIB') or os.path.join(_HERE, 'libiris.so')   # IRIS_LIB: experiment builds
 
 IRIS_OK, IRIS_ERR_INVALID, IRIS_ERR_CUDA, IRIS_ERR_EMPTY_RANGE, IRIS_ERR_STATE, \
     IRIS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,7 +75,8 @@ struct iris_ctx {
     Bank banks[3];
     DevBuf tw, whalf;
     // mel (CSR by mel bin)
-    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_nw = 0;
+    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_taps = 0;
+    int mel_L[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     DevBuf mel_info, mel_w;
     // plan
     bool has_plan = false, labels_done = false;
@@ -135,7 +137,8 @@ void fill_common(iris_ctx* c, FusedParams& p) {
     p.n_mel = c->n_mel;
     p.mel_f_lo = c->mel_f_lo;
     p.mel_f_n = c->mel_f_n;
-    p.mel_nw = c->mel_nw;
+    p.mel_taps = c->mel_taps;
+    for (int r = 0; r < 8; ++r) p.mel_L[r] = c->mel_L[r];
     p.mel_info = c->mel_info.as<uint32_t>();
     p.mel_w = c->mel_w.as<float>();
 }
@@ -288,10 +291,9 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     if (n_mel < 1 || n_mel > 128) return fail(IRIS_ERR_INVALID, "n_mel must be in [1, 128]");
     int rc = set_device(c);
     if (rc) return rc;
-    // every mel filter is stored as the contiguous bin range [start, start + len) that holds
-    // its non-zero weights (the triangles of linear_to_mel_weight_matrix are contiguous)
-    std::vector<uint32_t> info(n_mel, 0);
-    std::vector<float> fw;
+    // every mel filter is the contiguous bin range [lo, hi] that holds its non-zero weights
+    // (the triangles of linear_to_mel_weight_matrix are contiguous)
+    std::vector<int> lo_of(n_mel, -1), len_of(n_mel, 0);
     int f_lo = kBins, f_hi = -1;
     for (int m = 0; m < n_mel; ++m) {
         int lo = -1, hi = -1;
@@ -300,27 +302,47 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
                 if (lo < 0) lo = f;
                 hi = f;
             }
-        if (lo < 0) continue;   // empty filter: len 0
-        if (fw.size() + size_t(hi - lo + 1) >= (1u << 14))
-            return fail(IRIS_ERR_UNSUPPORTED, "mel matrix too dense for the fused projection");
-        info[m] = uint32_t(lo) | (uint32_t(hi - lo + 1) << 9) | (uint32_t(fw.size()) << 18);
-        for (int f = lo; f <= hi; ++f) fw.push_back(w[size_t(f) * n_mel + m]);
+        if (lo < 0) continue;   // empty filter
+        lo_of[m] = lo;
+        len_of[m] = hi - lo + 1;
         f_lo = std::min(f_lo, lo);
         f_hi = std::max(f_hi, hi);
     }
     if (f_hi < 0) { f_lo = 0; f_hi = 0; }
-    if (f_hi - f_lo + 1 > fused_max_mel_window() || int(fw.size()) > fused_max_mel_weights())
+    const int f_n = f_hi - f_lo + 1;
+    // groups of 16 filters share a trip count (the longest filter of the group); shorter
+    // filters are zero-padded and shifted so that every tap stays inside [f_lo, f_hi]
+    int L[8] = {0, 0, 0, 0, 0, 0, 0, 0}, taps = 0;
+    for (int m = 0; m < n_mel; ++m) L[m >> 4] = std::max(L[m >> 4], len_of[m]);
+    for (int r = 0; r < 8; ++r) taps += L[r];
+    if (f_n > fused_max_mel_window() || taps > fused_max_mel_taps())
         return fail(IRIS_ERR_UNSUPPORTED,
-                    "mel matrix spans more than 136 bins or holds more than 512 weights; use the "
-                    "unfused mel projection");
+                    "mel matrix spans more than 136 bins or needs more than 64 taps per lane; use "
+                    "the unfused mel projection");
+    std::vector<uint32_t> info(n_mel, 0);
+    std::vector<float> fw(size_t(std::max(taps, 1)) * 16, 0.f);
+    int row0 = 0;
+    for (int r = 0; r < 8; ++r) {
+        for (int l = 0; l < 16; ++l) {
+            const int m = 16 * r + l;
+            if (m >= n_mel || lo_of[m] < 0) continue;
+            const int start = std::min(lo_of[m] - f_lo, f_n - L[r]);
+            info[m] = uint32_t(start);
+            for (int i = 0; i < len_of[m]; ++i)
+                fw[size_t(row0 + (lo_of[m] - f_lo - start) + i) * 16 + l] =
+                    w[size_t(lo_of[m] + i) * n_mel + m];
+        }
+        row0 += L[r];
+    }
     CU(c->mel_info.reserve(info.size() * 4));
-    CU(c->mel_w.reserve(fw.size() * 4 + 4));
+    CU(c->mel_w.reserve(fw.size() * 4));
     CU(cudaMemcpy(c->mel_info.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice));
-    if (!fw.empty()) CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
-    c->mel_nw = int(fw.size());
+    CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
+    c->mel_taps = taps;
+    for (int r = 0; r < 8; ++r) c->mel_L[r] = L[r];
     c->n_mel = n_mel;
     c->mel_f_lo = f_lo;
-    c->mel_f_n = f_hi - f_lo + 1;
+    c->mel_f_n = f_n;
     return IRIS_OK;
 }
 
@@ -700,15 +722,18 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     if (mel) {
         p.do_log = mode != IRIS_FEAT_MEL;
         p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
-        if (p.do_minmax) {   // per-clip (~min, max) bit patterns + tiles-done counters; the
-                             // kernel leaves them zeroed, so only a fresh allocation is cleared
+        if (p.do_minmax) {   // per-clip (~min, max) bit patterns; k_logmel_post leaves them
+                             // zeroed, so only a fresh allocation is cleared
             const void* before = c->minmax.p;
-            CU(c->minmax.reserve(size_t(c->B) * 12));
+            CU(c->minmax.reserve(size_t(c->B) * 12));   // [B,2] min/max words + [B] post counters
             if (c->minmax.p != before) CU(cudaMemsetAsync(c->minmax.p, 0, c->minmax.cap, st));
             p.minmax = c->minmax.as<uint32_t>();
-            p.clip_done = p.minmax + 2 * size_t(c->B);
         }
         rc = timed_fused(c, p, FM_MEL, st);
+        if (rc) return rc;
+        if (p.do_minmax)
+            CU(launch_logmel_post(d_out, c->minmax.as<uint32_t>(), c->B,
+                                  size_t(c->n_mel) * c->T * c->C, 1, 1, st));
     } else {
         rc = timed_fused(c, p, mode, st);
     }

@@ -62,15 +62,17 @@ struct FusedParams {
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
     int32_t do_log, do_minmax;
-    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); zero between launches
-    uint32_t* clip_done;    // [B] tiles finished per clip; zero between launches
-    // mel projection: filter m covers bins [mel_start[m], +mel_len[m]) with weights at mel_woff[m]
+    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); k_logmel_post re-zeroes it
+    // mel projection: filters are handled in groups of 16 (m = lane + 16 r); every filter of
+    // group r reads mel_L[r] consecutive magnitudes starting at bin mel_f_lo + mel_info[m]
+    // (shorter filters are zero-padded), weights at mel_w[(row0(r) + i) * 16 + lane]
     int32_t n_mel;
     int32_t mel_f_lo;       // lowest bin with a non-zero weight
     int32_t mel_f_n;        // number of bins in [f_lo, f_hi]
-    int32_t mel_nw;         // number of stored weights
-    const uint32_t* mel_info;  // [n_mel] start | len << 9 | woff << 18
-    const float* mel_w;        // [mel_nw]
+    int32_t mel_taps;       // sum of mel_L
+    int32_t mel_L[8];
+    const uint32_t* mel_info;  // [n_mel] first tap, relative to mel_f_lo
+    const float* mel_w;        // [mel_taps][16]
     // tables
     const float4* tw4;      // [16][16] {W512^(n2*2m), W512^(n2*(2m+1))}
     const float* whalf;     // [512] 0.5 * hann

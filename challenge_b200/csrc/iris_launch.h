@@ -11,11 +11,11 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
 size_t fused_smem_bytes(const FusedParams& p, int mode);
 int fused_max_segments();      // mixing segments one clip may have
 int fused_max_mel_window();    // widest bin range [f_lo, f_hi] of the mel matrix
-int fused_max_mel_weights();   // stored mel weights
+int fused_max_mel_taps();      // sum over 16-filter groups of the longest filter
 size_t fused_tile_bytes(const FusedParams& p, int* stride_out);   // size of p.tile_blocks
 
 // k_post.cu
-cudaError_t launch_logmel_post(float* x, const uint32_t* minmax, int B, size_t per_clip, int do_minmax,
+cudaError_t launch_logmel_post(float* x, uint32_t* minmax, int B, size_t per_clip, int do_minmax,
                                int do_log, cudaStream_t stream);
 
 // k_bank.cu

@@ -1,4 +1,4 @@
-// Fused hot path (v3): gather + time-domain mix of the gained source frames (TMA bulk
+// Fused hot path (v4): gather + time-domain mix of the gained source frames (TMA bulk
 // copies into a 2-slot shared-memory ring), window, 512-point FFT per frame (two real
 // channels packed into one complex transform, one half-warp per FFT), then the epilogue
 // (SpecAugment masks, channel remap, stft_filter, complex / mag-phase / log-mag-phase
@@ -16,15 +16,20 @@
 // <= 2 channels, 2 for <= 4, ...): 16 half-warp FFT slots, 8 warps, 2 CTAs per SM.
 //  * k_tiles (one thread per tile) compacts, for every tile, the mixing segments that are
 //    kept and overlap it into a TileBlock (stage descriptors + the tile's mask bits).
-//  * k_fused CTAs claim tiles from a global counter (dynamic scheduling; a CTA that runs a
-//    clip's min-max tail simply claims fewer tiles) and stream the TileBlocks of the next
-//    tiles into a 4-deep shared-memory ring with cp.async, three tiles ahead.
+//  * k_fused CTAs claim tiles from a global counter (dynamic scheduling) and stream the
+//    TileBlocks of the next tiles into an 8-deep shared-memory ring with cp.async, three
+//    tiles ahead; every ring entry has an mbarrier that completes when its block has landed.
 //  * Every stage of a tile is (FR+1) 2 KB rows per pair, fetched with one cp.async.bulk per
 //    pair into slot (stage & 1) and consumed by all 8 warps.  There is no producer warp: the
 //    LAST warp to finish reading a slot (shared-memory counter) issues the copy of stage+2
 //    into it, so loads run two stages ahead while the FFTs execute.
-//  * LOGMEL_MINMAX: per-tile min/max go to global atomics; the CTA that completes a clip
-//    (per-clip tile counter) normalises and logs the clip in place while it is still in L2.
+//  * There is NO CTA-wide barrier in the tile loop: warps are coupled only through the slot
+//    protocol (a warp runs at most two stages ahead of the slowest one), so mix, FFT and
+//    epilogue phases of different warps overlap.  Every warp stores its own frames.
+//  * LOGMEL_MINMAX: per-warp min/max go to global atomics; k_logmel_post (k_post.cu)
+//    normalises and logs the batch in place right after, while it is still in L2.  (An
+//    in-kernel tail run by the CTA that completes a clip was measured 35 % slower: the CTA
+//    that falls behind becomes the last finisher of every clip it touches.)
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
@@ -33,11 +38,10 @@ namespace iris {
 constexpr int kSlots = 16;       // half-warp FFT slots per CTA
 constexpr int kWarps = 8;
 constexpr int kThreads = 256;
-constexpr int kRing = 4;         // TileBlocks in flight per CTA
-constexpr int kMelPad = 34;      // mel tile row stride in floats (conflict-free float2 columns)
-constexpr int kMaxStages = 32;   // mixing segments of one clip (upper bound on stages per tile)
+constexpr int kRing = 8;         // TileBlock ring entries per CTA (>= 6: see the skew bound below)
+constexpr int kMaxStages = 16;   // mixing segments of one clip (upper bound on stages per tile)
 constexpr int kMaxMel = 128;
-constexpr int kMaxMelW = 512;
+constexpr int kMaxTaps = 64;     // sum over the 16-filter groups of the longest filter in the group
 
 struct StageDesc {
     const float* src;      // first row of pair plane (group * NP) of the source
@@ -60,30 +64,32 @@ static_assert(sizeof(TileBlock) == 32 + 24 * kMaxStages, "TileBlock layout");
 constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
 // ---- shared memory map (bytes) ----
-constexpr int OFF_FULL = 0;      // uint64 full[2]
-constexpr int OFF_CNT = 16;      // int cnt[2]
-constexpr int OFF_CLAIM = 32;    // int claimed[8]
+constexpr int OFF_FULL = 0;      // uint64 full[2]      slot s holds a complete stage
+constexpr int OFF_CNT = 16;      // int cnt[2]          warps done reading slot s
+constexpr int OFF_CLAIM = 32;    // int claimed[3]      first tiles of the CTA
+constexpr int OFF_RFULL = 64;    // uint64 rfull[8]     ring entry k & 7 has landed
 constexpr int OFF_RING = 128;
 constexpr int OFF_TW = OFF_RING + kRing * kTileBlockBytes;
 constexpr int OFF_WH = OFF_TW + 256 * 16;
 constexpr int OFF_MINFO = OFF_WH + 512 * 4;
 constexpr int OFF_MW = OFF_MINFO + kMaxMel * 4;
-constexpr int OFF_XCH = OFF_MW + kMaxMelW * 4;
+constexpr int OFF_XCH = OFF_MW + kMaxTaps * 16 * 4;
 constexpr int OFF_SLOTS = OFF_XCH + kSlots * kXchSlotFloats * 4;
 static_assert(OFF_SLOTS % 128 == 0, "slot alignment");
 
 __host__ __device__ inline uint32_t slot_bytes(int np_shift) {
     return (1u << np_shift) * ((16u >> np_shift) + 1u) * 2048u;
 }
-__host__ __device__ inline uint32_t smem_total(int np_shift, bool mel, int n_mel) {
-    return OFF_SLOTS + 2 * slot_bytes(np_shift) + (mel ? uint32_t(n_mel) * kMelPad * 4 : 0);
+__host__ __device__ inline uint32_t smem_total(int np_shift) {
+    return OFF_SLOTS + 2 * slot_bytes(np_shift);
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;" ::: "memory");
+// arrive on an mbarrier once all cp.async of this thread issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ---- pre-kernel: one thread per tile builds its TileBlock ----
@@ -230,55 +236,6 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
     }
 }
 
-// min-max + log of one finished clip, in place (data_utils.py:37-55), by the whole CTA:
-// (x - min) / max(max - min, 1e-8), then log(x + 1e-8).  Reads bypass L1 (other CTAs wrote).
-__device__ __noinline__ void clip_tail(const FusedParams& p, int b) {
-    const int tid = threadIdx.x;
-    const float lo = __uint_as_float(~__ldcg(&p.minmax[2 * b]));
-    const float hi = __uint_as_float(__ldcg(&p.minmax[2 * b + 1]));
-    const float den = fmaxf(hi - lo, 1e-8f);
-    const size_t per = size_t(p.n_mel) * p.T * p.C;
-    float* base = p.out + size_t(b) * per;
-    const bool lg = p.do_log != 0;
-    if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-        float4* v4 = reinterpret_cast<float4*>(base);
-        const int n4 = int(per >> 2);
-        for (int i = tid; i < n4; i += 4 * kThreads) {
-            float4 a[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * kThreads < n4) a[u] = __ldcg(v4 + i + u * kThreads);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (i + u * kThreads < n4) {
-                    a[u].x = __fdividef(a[u].x - lo, den);
-                    a[u].y = __fdividef(a[u].y - lo, den);
-                    a[u].z = __fdividef(a[u].z - lo, den);
-                    a[u].w = __fdividef(a[u].w - lo, den);
-                    if (lg) {
-                        a[u].x = __logf(a[u].x + 1e-8f);
-                        a[u].y = __logf(a[u].y + 1e-8f);
-                        a[u].z = __logf(a[u].z + 1e-8f);
-                        a[u].w = __logf(a[u].w + 1e-8f);
-                    }
-                    v4[i + u * kThreads] = a[u];
-                }
-            }
-        }
-    } else {
-        for (size_t i = tid; i < per; i += kThreads) {
-            float a = __fdividef(__ldcg(base + i) - lo, den);
-            base[i] = lg ? __logf(a + 1e-8f) : a;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {   // leave the per-clip scratch zeroed for the next launch
-        p.minmax[2 * b] = 0u;
-        p.minmax[2 * b + 1] = 0u;
-        p.clip_done[b] = 0u;
-    }
-}
-
 // KB: number of 32-bin groups the epilogue needs (mel support below bin 32*KB); 8 = all bins.
 template <int MODE, int KB>
 __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ FusedParams p) {
@@ -288,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
     const int warp = tid >> 5, lane = tid & 31, n2 = lane & 15;
     const uint32_t sm_base = smem_u32(sm);
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
+    uint64_t* rfull = reinterpret_cast<uint64_t*>(sm + OFF_RFULL);
     int* cnt = reinterpret_cast<int*>(sm + OFF_CNT);
     int* claimed = reinterpret_cast<int*>(sm + OFF_CLAIM);
     float4* s_tw4 = reinterpret_cast<float4*>(sm + OFF_TW);
@@ -299,53 +257,65 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
     };
     const int NP = 1 << p.np_shift;
     const int FR = 16 >> p.np_shift;
-    const int per_clip = ((p.T + FR - 1) / FR) * p.n_groups;
-    const int n_tiles = p.B * per_clip;
+    const int n_tiles = p.B * ((p.T + FR - 1) / FR) * p.n_groups;
     const uint32_t slotB = slot_bytes(p.np_shift);
     const uint32_t planeB = uint32_t(FR + 1) * 2048u;
 
-    // one warp streams the TileBlock of `tile` into ring entry k (or writes the end marker)
+    // one warp streams the TileBlock of `tile` into ring entry k (or writes the end marker);
+    // completion is signalled later by fetch_done(k) (32 arrivals on rfull[k & 7])
     auto fetch_block = [&](int k, int tile) {
         TileBlock* dst = ring(k);
         if (tile < n_tiles) {
             const unsigned char* src = p.tile_blocks + size_t(tile) * p.tile_stride;
             const uint32_t d0 = smem_u32(dst);
             for (int c = lane * 16; c < p.tile_stride; c += 32 * 16) cp_async16(d0 + c, src + c);
-        } else if (lane == 0) {
-            dst->n = 0;
+        } else {
+            if (lane == 0) dst->n = 0;
+            __threadfence_block();
         }
     };
+    auto fetch_done = [&](int k) { cp_async_arrive(&rfull[k & (kRing - 1)]); };
 
     for (int i = tid; i < 256; i += kThreads) s_tw4[i] = p.tw4[i];
     for (int i = tid; i < 512; i += kThreads) s_wh[i] = p.whalf[i];
     if (kMel) {
-        for (int i = tid; i < p.n_mel; i += kThreads) s_minfo[i] = p.mel_info[i];
-        for (int i = tid; i < p.mel_nw; i += kThreads) s_mw[i] = p.mel_w[i];
+        for (int i = tid; i < kMaxMel; i += kThreads) s_minfo[i] = i < p.n_mel ? p.mel_info[i] : 0u;
+        for (int i = tid; i < p.mel_taps * 16; i += kThreads) s_mw[i] = p.mel_w[i];
     }
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
+        for (int i = 0; i < kRing; ++i) mbar_init(&rfull[i], 32);
         cnt[0] = 0;
         cnt[1] = 0;
         fence_mbar_init();
-        // the first four tiles of this CTA, in order (an end marker must never precede work)
-        const int c = int(atomicAdd(&p.sched[0], 4u));
-        for (int i = 0; i < 4; ++i) claimed[i] = c + i;
+        // the first three tiles of this CTA, in order (an end marker must never precede work)
+        const int c = int(atomicAdd(&p.sched[0], 3u));
+        for (int i = 0; i < 3; ++i) claimed[i] = c + i;
     }
     __syncthreads();
     if (warp < 3) {
         fetch_block(warp, claimed[warp]);
-        cp_async_wait_all();
+        fetch_done(warp);
     }
-    __syncthreads();
 
+    // ring entries 0 .. ready are known to have landed (per warp; entries land in order)
+    int ready = -1;
+    auto ensure = [&](int k) {
+        while (ready < k) {
+            ++ready;
+            mbar_wait(&rfull[ready & (kRing - 1)], uint32_t(ready >> 3) & 1u);
+        }
+    };
     // issue cursor = position (tile iteration ki, entry ei) of stage q + 2
     int ki = 0, ei = 0;
     auto advance = [&]() {
+        ensure(ki);
         const int n = ring(ki)->n;
         if (n != 0 && ++ei >= n) { ++ki; ei = 0; }
     };
     auto np_of = [&](int k) { return min(NP, p.n_pairs - ((ring(k)->t0_group >> 24) << p.np_shift)); };
+    ensure(1);
     if (tid == 0) {
         int a = 0, e = 0;
         for (int s = 0; s < 2; ++s) {
@@ -366,49 +336,61 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
     const int j = slot >> p.np_shift;          // tile-relative frame of this slot
     const int pr = slot & (NP - 1);            // pair within the tile's group
     const float2* my_rows = reinterpret_cast<const float2*>(sm + OFF_SLOTS + pr * planeB) + j * 256 + n2;
-    float* meltile = reinterpret_cast<float*>(sm + OFF_SLOTS + 2 * slotB);
+    // running per-clip extrema of this lane (flushed when the clip changes)
+    float mn = __int_as_float(0x7f800000), mx = 0.f;
+    int mm_clip = -1;
+    auto flush_minmax = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0 && mn <= mx) {
+            atomicMax(&p.minmax[2 * mm_clip], ~__float_as_uint(mn));
+            atomicMax(&p.minmax[2 * mm_clip + 1], __float_as_uint(mx));
+        }
+        mn = __int_as_float(0x7f800000);
+        mx = 0.f;
+    };
 
     int q = 0;          // stages consumed so far
-    int pend = 0;       // thread 0: this CTA completed clip b_prev (min-max tail pending)
-    int b_prev = 0;
     for (int k = 0;; ++k) {
+        ensure(k);
         const TileBlock* tb = ring(k);
         const int n_st = tb->n;
         if (n_st == 0) break;
+        // Skew bound: a slot is refilled only after all 8 warps have read it and every tile
+        // has at least one stage, so no warp is more than two tiles ahead of the slowest one;
+        // entry k+3 therefore never overwrites an entry (>= k-2) that is still being read.
         int new_claim = 0;
-        const bool builder = warp == (k & (kWarps - 1));
-        if (builder) {   // stream the block of tile k+3, claim the tile of iteration k+4
-            fetch_block(k + 3, claimed[(k + 3) & 7]);
-            if (lane == 0) new_claim = int(atomicAdd(&p.sched[0], 1u));
-        }
+        // one fixed builder warp: its claims are then ordered like the ring entries (an end
+        // marker must never precede a valid tile)
+        const bool builder = warp == 0;
+        // the builder warp of this iteration claims the tile of ring entry k+3 now and streams
+        // its block at the end of the iteration, when the atomic has long returned
+        if (builder && lane == 0) new_claim = int(atomicAdd(&p.sched[0], 1u));
 
+        // ---- gather + mix: acc = sum over the stages of this tile of gain * frame ----
         float re[32], im[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
-
-        // ---- gather + mix: acc += gain * frame_k of every stage of this tile ----
         const int group = tb->t0_group >> 24;
         const bool pair_ok = (group << p.np_shift) + pr < p.n_pairs;
-        for (int e = 0; e < n_st; ++e) {
-            const int s = q & 1;
+        // wait for stage e of this tile; returns the gain, or sets active = false
+        auto stage_begin = [&](int e, bool& active) -> float {
             const uint32_t jj = *reinterpret_cast<const uint32_t*>(&tb->d[e].j_lo);   // j_lo | j_cnt << 16
             const float gn = tb->d[e].gain;
-            mbar_wait(&full[s], uint32_t(q >> 1) & 1u);
-            if (pair_ok && unsigned(j - int(jj & 0xffffu)) < (jj >> 16)) {
-                const float2* src = reinterpret_cast<const float2*>(
-                    reinterpret_cast<const unsigned char*>(my_rows) + s * slotB);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float2 x = src[16 * i];
-                    re[i] = fmaf(gn, x.x, re[i]);
-                    im[i] = fmaf(gn, x.y, im[i]);
-                }
-            }
+            mbar_wait(&full[q & 1], uint32_t(q >> 1) & 1u);
+            active = pair_ok && unsigned(j - int(jj & 0xffffu)) < (jj >> 16);
+            return gn;
+        };
+        // this warp is done reading the slot; the last warp to say so refills it
+        auto stage_end = [&]() {
+            const int s = q & 1;
             __syncwarp();
             if (lane == 0) {
                 const int old = atomicAdd(&cnt[s], 1);
-                if (old == kWarps - 1) {          // last reader of the slot: refill it
+                if (old == kWarps - 1) {
                     cnt[s] = 0;
+                    if (ready < ki) mbar_wait(&rfull[ki & (kRing - 1)], uint32_t(ki >> 3) & 1u);
                     const TileBlock* nb = ring(ki);
                     if (nb->n != 0) {
                         fence_proxy_async();
@@ -419,6 +401,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
             }
             ++q;
             advance();
+        };
+        {   // first stage initialises the accumulators
+            bool active;
+            const float gn = stage_begin(0, active);
+            const float2* src = reinterpret_cast<const float2*>(
+                reinterpret_cast<const unsigned char*>(my_rows) + (q & 1) * slotB);
+            const float g0 = active ? gn : 0.f;
+            if (!active) src = reinterpret_cast<const float2*>(sm + OFF_TW);   // 4 KB of finite data
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float2 x = src[16 * i];
+                re[i] = g0 * x.x;
+                im[i] = g0 * x.y;
+            }
+            stage_end();
+        }
+        for (int e = 1; e < n_st; ++e) {
+            bool active;
+            const float gn = stage_begin(e, active);
+            if (active) {
+                const float2* src = reinterpret_cast<const float2*>(
+                    reinterpret_cast<const unsigned char*>(my_rows) + (q & 1) * slotB);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float2 x = src[16 * i];
+                    re[i] = fmaf(gn, x.x, re[i]);
+                    im[i] = fmaf(gn, x.y, im[i]);
+                }
+            }
+            stage_end();
         }
 
         const int b = tb->b;
@@ -485,6 +497,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
         // bin f = kb+32*k2 pairs with Za[15-k2] (lane 0: Zb[15-k2]).  The 0.5 of the
         // two-channel split is folded into the window table.
         if (kMel) {
+            if (p.do_minmax && b != mm_clip) {
+                if (mm_clip >= 0) flush_minmax();
+                mm_clip = b;
+            }
             float2* mg = reinterpret_cast<float2*>(xs);   // [mel_f_n] (|ch0|, |ch1|), aliases the exchange slot
             const int f_lo = p.mel_f_lo, f_n = p.mel_f_n;
             float acc0[8], acc1[8];   // mel bins m = n2 + 16 r
@@ -523,174 +539,122 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                     }
                     __syncwarp(hmask);
                 }
-                const int n_r = (p.n_mel + 15) >> 4;
+                // sparse mel projection (transforms.py:51-77): filter m = n2 + 16 r reads
+                // mel_L[r] taps starting at its first bin; shorter filters are zero-padded, so
+                // the trip count is uniform across the half-warp
+                const float* wr = s_mw + n2;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int m = n2 + 16 * r;
-                    if (r < n_r && m < p.n_mel) {
-                        const uint32_t info = s_minfo[m];
-                        const float2* a = mg + (int(info & 511u) - f_lo);
-                        const int len = int((info >> 9) & 511u);
-                        const float* w = s_mw + (info >> 18);
-                        for (int i = 0; i < len; ++i) {
-                            const float2 x = a[i];
-                            acc0[r] = fmaf(w[i], x.x, acc0[r]);
-                            acc1[r] = fmaf(w[i], x.y, acc1[r]);
-                        }
+                    const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 16)
+                    const float2* a = mg + s_minfo[n2 + 16 * r];
+                    for (int i = 0; i < L; ++i) {
+                        const float2 x = a[i];
+                        const float w = wr[16 * i];
+                        acc0[r] = fmaf(w, x.x, acc0[r]);
+                        acc1[r] = fmaf(w, x.y, acc1[r]);
                     }
+                    wr += 16 * L;
                 }
             }
-            __syncwarp();
-            // ---- tile of mel values [n_mel][FR frames x C channels] in shared memory ----
-            const int C = p.C;
+            // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
             if (in_range) {
-                const int col = j * C + 2 * pr;
+                const int C = p.C;
+                float* o = p.out + (size_t(b) * p.n_mel * p.T + t) * C + 2 * pair + size_t(n2) * p.T * C;
+                const int rs16 = 16 * p.T * C;
+                const bool lg = p.do_log && !p.do_minmax;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int m = n2 + 16 * r;
-                    if (m < p.n_mel) {
-                        if ((C & 1) == 0) {
-                            *reinterpret_cast<float2*>(meltile + m * kMelPad + col) = make_float2(acc0[r], acc1[r]);
-                        } else {
-                            meltile[m * kMelPad + col] = acc0[r];
-                            if (has1) meltile[m * kMelPad + col + 1] = acc1[r];
+                    if (n2 + 16 * r < p.n_mel) {
+                        float a0 = acc0[r], a1 = acc1[r];
+                        if (p.do_minmax) {
+                            mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
+                            mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
                         }
-                    }
-                }
-            }
-            if (builder) {
-                cp_async_wait_all();
-                if (lane == 0) claimed[(k + 4) & 7] = new_claim;
-            }
-            // tile complete (also publishes the builder's ring entry); with min-max, learn
-            // whether this CTA completed the previous tile's clip
-            int tail = 0;
-            if (p.do_minmax) tail = __syncthreads_or(pend);
-            else __syncthreads();
-            if (tail) clip_tail(p, b_prev);
-            // coalesced store [B, n_mel, T, C] (+ log) and per-clip min/max (data_utils.py:37-55)
-            const int ncols = min(FR, p.T - t0) * C;
-            float mn = __int_as_float(0x7f800000), mx = 0.f;
-            float* orow = p.out + (size_t(b) * p.n_mel * p.T + t0) * C;
-            const bool lg = p.do_log && !p.do_minmax;
-            if ((C & 1) == 0) {
-                const int c2 = tid & 15;
-                if (2 * c2 < ncols) {
-                    for (int m = tid >> 4; m < p.n_mel; m += kThreads / 16) {
-                        float2 vv = *reinterpret_cast<const float2*>(meltile + m * kMelPad + 2 * c2);
-                        mn = fminf(mn, fminf(vv.x, vv.y));
-                        mx = fmaxf(mx, fmaxf(vv.x, vv.y));
                         if (lg) {
-                            vv.x = __logf(vv.x + 1e-8f);
-                            vv.y = __logf(vv.y + 1e-8f);
+                            a0 = __logf(a0 + 1e-8f);
+                            a1 = __logf(a1 + 1e-8f);
                         }
-                        *reinterpret_cast<float2*>(orow + size_t(m) * p.T * C + 2 * c2) = vv;
-                    }
-                }
-            } else {
-                const int c1 = tid & 31;
-                if (c1 < ncols) {
-                    for (int m = tid >> 5; m < p.n_mel; m += kThreads / 32) {
-                        float vv = meltile[m * kMelPad + c1];
-                        mn = fminf(mn, vv);
-                        mx = fmaxf(mx, vv);
-                        if (lg) vv = __logf(vv + 1e-8f);
-                        orow[size_t(m) * p.T * C + c1] = vv;
+                        if ((C & 1) == 0) {
+                            *reinterpret_cast<float2*>(o + r * rs16) = make_float2(a0, a1);
+                        } else {
+                            o[r * rs16] = a0;
+                            if (has1) o[r * rs16 + 1] = a1;
+                        }
                     }
                 }
             }
-            if (p.do_minmax) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                if (lane == 0 && mn <= mx) {
-                    atomicMax(&p.minmax[2 * b], ~__float_as_uint(mn));
-                    atomicMax(&p.minmax[2 * b + 1], __float_as_uint(mx));
-                }
-            }
-            __syncthreads();   // store phase over: the mel tile and ring entry k may be reused
-            if (p.do_minmax) {
-                if (tid == 0) {
-                    __threadfence();
-                    const unsigned old = atomicAdd(&p.clip_done[b], 1u);
-                    pend = (old == unsigned(per_clip) - 1u) ? 1 : 0;
-                    if (pend) __threadfence();
-                }
-                b_prev = b;
-            }
-        } else {
-            if (MODE == FM_ACTIVITY) {
-                // frame "active" iff any STFT coefficient (any bin, re or im, any channel) > 0
-                // (pipeline.py:55)
-                float mxv = 0.f;
-                if (do_fft) {
-                    auto emit = [&](cpx zf, cpx zm) {
-                        mxv = fmaxf(mxv, fmaxf(fmaxf(zf.x + zm.x, zf.y - zm.y),
-                                               fmaxf(zf.y + zm.y, zm.x - zf.x)));
-                    };
-#pragma unroll
-                    for (int k2 = 0; k2 < 8; ++k2) {
-                        const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
-                        const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
-                        emit(Za[k2], pa);
-                        emit(Zb[k2], pb);
-                    }
-                    if (l0) emit(Za[8], Za[8]);
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(hmask, mxv, o));
-                if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
-            } else if (do_fft) {
-                // per-lane bitmap of frequency-masked bins: bit k2 -> ka + 32*k2,
-                // bit 8 + k2 -> kb + 32*k2, bit 16 -> bin 256
-                uint32_t zbits = 0;
-                for (int i = 0; i < p.n_fmask; ++i) {
-                    const int size = tb->fm[2 * i], off = tb->fm[2 * i + 1];
-#pragma unroll
-                    for (int k2 = 0; k2 < 8; ++k2) {
-                        if (unsigned(ka + 32 * k2 - off) < unsigned(size)) zbits |= 1u << k2;
-                        if (unsigned(kb + 32 * k2 - off) < unsigned(size)) zbits |= 1u << (8 + k2);
-                    }
-                    if (unsigned(256 - off) < unsigned(size)) zbits |= 1u << 16;
-                }
+        } else if (MODE == FM_ACTIVITY) {
+            // frame "active" iff any STFT coefficient (any bin, re or im, any channel) > 0
+            // (pipeline.py:55)
+            float mxv = 0.f;
+            if (do_fft) {
+                auto emit = [&](cpx zf, cpx zm) {
+                    mxv = fmaxf(mxv, fmaxf(fmaxf(zf.x + zm.x, zf.y - zm.y),
+                                           fmaxf(zf.y + zm.y, zm.x - zf.x)));
+                };
 #pragma unroll
                 for (int k2 = 0; k2 < 8; ++k2) {
                     const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
                     const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
-                    {
-                        const int f = ka + 32 * k2;
-                        const cpx zf = Za[k2];
-                        store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pa.x, zf.y - pa.y,
-                                        zf.y + pa.y, pa.x - zf.x, ((zbits >> k2) & 1u) ? 0.f : mt);
-                    }
-                    {
-                        const int f = kb + 32 * k2;
-                        const cpx zf = Zb[k2];
-                        store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pb.x, zf.y - pb.y,
-                                        zf.y + pb.y, pb.x - zf.x, ((zbits >> (8 + k2)) & 1u) ? 0.f : mt);
-                    }
+                    emit(Za[k2], pa);
+                    emit(Zb[k2], pb);
                 }
-                if (l0) {
-                    const cpx zf = Za[8];
-                    store_bin<MODE>(p, b, 256, t, pair, has1, zf.x + zf.x, zf.y - zf.y,
-                                    zf.y + zf.y, zf.x - zf.x, ((zbits >> 16) & 1u) ? 0.f : mt);
+                if (l0) emit(Za[8], Za[8]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(hmask, mxv, o));
+            if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
+        } else if (do_fft) {
+            // per-lane bitmap of frequency-masked bins: bit k2 -> ka + 32*k2,
+            // bit 8 + k2 -> kb + 32*k2, bit 16 -> bin 256
+            uint32_t zbits = 0;
+            for (int i = 0; i < p.n_fmask; ++i) {
+                const int size = tb->fm[2 * i], off = tb->fm[2 * i + 1];
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    if (unsigned(ka + 32 * k2 - off) < unsigned(size)) zbits |= 1u << k2;
+                    if (unsigned(kb + 32 * k2 - off) < unsigned(size)) zbits |= 1u << (8 + k2);
+                }
+                if (unsigned(256 - off) < unsigned(size)) zbits |= 1u << 16;
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
+                const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
+                {
+                    const int f = ka + 32 * k2;
+                    const cpx zf = Za[k2];
+                    store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pa.x, zf.y - pa.y,
+                                    zf.y + pa.y, pa.x - zf.x, ((zbits >> k2) & 1u) ? 0.f : mt);
+                }
+                {
+                    const int f = kb + 32 * k2;
+                    const cpx zf = Zb[k2];
+                    store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pb.x, zf.y - pb.y,
+                                    zf.y + pb.y, pb.x - zf.x, ((zbits >> (8 + k2)) & 1u) ? 0.f : mt);
                 }
             }
-            if (builder) {
-                cp_async_wait_all();
-                if (lane == 0) claimed[(k + 4) & 7] = new_claim;
+            if (l0) {
+                const cpx zf = Za[8];
+                store_bin<MODE>(p, b, 256, t, pair, has1, zf.x + zf.x, zf.y - zf.y,
+                                zf.y + zf.y, zf.x - zf.x, ((zbits >> 16) & 1u) ? 0.f : mt);
             }
-            __syncthreads();   // ring entry k may be reused; publishes the builder's ring entry
         }
+        if (builder) {
+            fetch_block(k + 3, __shfl_sync(0xffffffffu, new_claim, 0));
+            fetch_done(k + 3);
+        }
+#ifndef IRIS_NO_TILE_BARRIER
+        // Not needed for correctness: keeps the 8 warps in the same phase, so that the slots are
+        // drained (and refilled) at the start of a tile and the loads fly during the FFTs.
+        // Measured on cfg2: 357 us with, 376 us without (COMPLEX: 457 vs 639 us).
+        __syncthreads();
+#endif
     }
-    if (kMel && p.do_minmax) {
-        if (__syncthreads_or(pend)) clip_tail(p, b_prev);
-    }
+    if (kMel && p.do_minmax && mm_clip >= 0) flush_minmax();
     // the last CTA to leave resets the tile scheduler for the next launch
+    __syncthreads();
     if (tid == 0) {
-        __threadfence();
         if (atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
             p.sched[0] = 0u;
             p.sched[1] = 0u;
@@ -698,12 +662,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
     }
 }
 
-size_t fused_smem_bytes(const FusedParams& p, int mode) {
-    return smem_total(p.np_shift, mode == FM_MEL, p.n_mel);
-}
+size_t fused_smem_bytes(const FusedParams& p, int) { return smem_total(p.np_shift); }
 int fused_max_segments() { return kMaxStages; }
 int fused_max_mel_window() { return kXchSlotFloats / 2; }
-int fused_max_mel_weights() { return kMaxMelW; }
+int fused_max_mel_taps() { return kMaxTaps; }
 size_t fused_tile_bytes(const FusedParams& p, int* stride_out) {
     const int FR = 16 >> p.np_shift;
     const long long n_tiles = (long long)p.B * p.n_groups * ((p.T + FR - 1) / FR);
