@@ -50,7 +50,7 @@ SIGNATURES = {
                             C.c_void_p]),
     'iris_metric_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p]),
+                                     C.c_void_p, C.c_void_p]),
     'iris_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'iris_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i32p, C.c_int]),
     'iris_plan_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64),

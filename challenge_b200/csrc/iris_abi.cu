@@ -315,9 +315,11 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     int L[8] = {0, 0, 0, 0, 0, 0, 0, 0}, taps = 0;
     for (int m = 0; m < n_mel; ++m) L[m >> 4] = std::max(L[m >> 4], len_of[m]);
     for (int r = 0; r < 8; ++r) taps += L[r];
-    if (f_n > fused_max_mel_window() || taps > fused_max_mel_taps())
+    bool long_filter = false;
+    for (int r = 0; r < 8; ++r) long_filter = long_filter || L[r] > 12;
+    if (f_n > fused_max_mel_window() || taps > fused_max_mel_taps() || long_filter)
         return fail(IRIS_ERR_UNSUPPORTED,
-                    "mel matrix spans more than 136 bins or needs more than 64 taps per lane; use "
+                    "mel matrix spans more than 136 bins or has a filter wider than 12 bins; use "
                     "the unfused mel projection");
     std::vector<uint32_t> info(n_mel, 0);
     std::vector<float> fw(size_t(std::max(taps, 1)) * 16, 0.f);
@@ -777,15 +779,16 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
 }
 
 int iris_metric_counts(iris_ctx* c, const float* y_true, const float* y_pred, int B, int T, int K,
-                       float thr, int32_t* d_triples, uint64_t* d_tpfpfn, float* d_er,
-                       iris_stream stream) {
+                       float thr, int32_t* d_triples, uint64_t* d_tpfpfn, uint64_t* d_sums,
+                       float* d_er, iris_stream stream) {
     if (!c || !y_true || !y_pred || !d_triples) return fail(IRIS_ERR_INVALID, "NULL argument");
     if (B < 1 || T < 1 || K < 1) return fail(IRIS_ERR_INVALID, "bad shape");
     int rc = set_device(c);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(launch_metric_counts(y_true, y_pred, B, T, K, thr, d_triples,
-                            reinterpret_cast<unsigned long long*>(d_tpfpfn), st));
+                            reinterpret_cast<unsigned long long*>(d_tpfpfn),
+                            reinterpret_cast<unsigned long long*>(d_sums), st));
     if (d_er) CU(launch_er_finalize(d_triples, B, d_er, st));
     return IRIS_OK;
 }

@@ -42,7 +42,7 @@ cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream);
 // k_metrics.cu
 cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int K,
                                  float threshold, int32_t* triples, unsigned long long* tpfpfn,
-                                 cudaStream_t stream);
+                                 unsigned long long* sums, cudaStream_t stream);
 cudaError_t launch_er_finalize(const int32_t* triples, int B, float* er, cudaStream_t stream);
 
 }  // namespace iris

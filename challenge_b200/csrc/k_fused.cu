@@ -487,8 +487,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                     }
                 }
                 __syncwarp(hmask);
+                // Za is complete after round 1: transform it now, while only v[16..31] is
+                // still live, instead of holding v, Za and Zb together
+                if (rho == 1) Fft<16>::run(Za);
             }
-            Fft<16>::run(Za);
             Fft<16>::run(Zb);
         }
 
@@ -543,18 +545,35 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 // mel_L[r] taps starting at its first bin; shorter filters are zero-padded, so
                 // the trip count is uniform across the half-warp
                 const float* wr = s_mw + n2;
+#define IRIS_TAP(i)                                            \
+    {                                                          \
+        const float2 x = a[i];                                 \
+        const float w = wr[16 * (i)];                          \
+        acc0[r] = fmaf(w, x.x, acc0[r]);                       \
+        acc1[r] = fmaf(w, x.y, acc1[r]);                       \
+    }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 16)
+                    const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 16); uniform
                     const float2* a = mg + s_minfo[n2 + 16 * r];
-                    for (int i = 0; i < L; ++i) {
-                        const float2 x = a[i];
-                        const float w = wr[16 * i];
-                        acc0[r] = fmaf(w, x.x, acc0[r]);
-                        acc1[r] = fmaf(w, x.y, acc1[r]);
+                    switch (L) {   // one uniform jump, then straight-line taps
+                        case 12: IRIS_TAP(11)
+                        case 11: IRIS_TAP(10)
+                        case 10: IRIS_TAP(9)
+                        case 9: IRIS_TAP(8)
+                        case 8: IRIS_TAP(7)
+                        case 7: IRIS_TAP(6)
+                        case 6: IRIS_TAP(5)
+                        case 5: IRIS_TAP(4)
+                        case 4: IRIS_TAP(3)
+                        case 3: IRIS_TAP(2)
+                        case 2: IRIS_TAP(1)
+                        case 1: IRIS_TAP(0)
+                        default: break;
                     }
                     wr += 16 * L;
                 }
+#undef IRIS_TAP
             }
             // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
             if (in_range) {
@@ -562,25 +581,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ F
                 float* o = p.out + (size_t(b) * p.n_mel * p.T + t) * C + 2 * pair + size_t(n2) * p.T * C;
                 const int rs16 = 16 * p.T * C;
                 const bool lg = p.do_log && !p.do_minmax;
+                const int n_r = (p.n_mel + 15) >> 4;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    if (n2 + 16 * r < p.n_mel) {
-                        float a0 = acc0[r], a1 = acc1[r];
-                        if (p.do_minmax) {
-                            mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
-                            mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
-                        }
-                        if (lg) {
-                            a0 = __logf(a0 + 1e-8f);
-                            a1 = __logf(a1 + 1e-8f);
-                        }
-                        if ((C & 1) == 0) {
-                            *reinterpret_cast<float2*>(o + r * rs16) = make_float2(a0, a1);
-                        } else {
-                            o[r * rs16] = a0;
-                            if (has1) o[r * rs16 + 1] = a1;
-                        }
+                    if (r >= n_r) break;                                  // uniform
+                    if (r == n_r - 1 && n2 + 16 * r >= p.n_mel) break;    // ragged last group
+                    float a0 = acc0[r], a1 = acc1[r];
+                    if (p.do_minmax) {
+                        mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
+                        mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
                     }
+                    if (lg) {
+                        a0 = __logf(a0 + 1e-8f);
+                        a1 = __logf(a1 + 1e-8f);
+                    }
+                    if ((C & 1) == 0) {
+                        *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                    } else {
+                        o[0] = a0;
+                        if (has1) o[1] = a1;
+                    }
+                    o += rs16;
                 }
             }
         } else if (MODE == FM_ACTIVITY) {

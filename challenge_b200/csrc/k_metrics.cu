@@ -26,7 +26,8 @@ __device__ __forceinline__ int run_start(const uint32_t* bits, int e) {
 __global__ void __launch_bounds__(128) k_metric_counts(const float* __restrict__ y_true,
                                                        const float* __restrict__ y_pred, int T,
                                                        int K, float thr, int32_t* triples,
-                                                       unsigned long long* tpfpfn) {
+                                                       unsigned long long* tpfpfn,
+                                                       unsigned long long* sums) {
     extern __shared__ uint32_t s_bits[];
     const int W = (T + 31) >> 5;
     uint32_t* tb = s_bits;               // [K][W] y_true >= thr
@@ -125,6 +126,11 @@ __global__ void __launch_bounds__(128) k_metric_counts(const float* __restrict__
             if (s_cnt[4]) atomicAdd(&tpfpfn[1], (unsigned long long)s_cnt[4]);
             if (s_cnt[5]) atomicAdd(&tpfpfn[2], (unsigned long long)s_cnt[5]);
         }
+        if (sums) {   // batch totals of (n_true, n_pred, correct): the all-reduce payload
+            if (s_cnt[0]) atomicAdd(&sums[0], (unsigned long long)s_cnt[0]);
+            if (s_cnt[1]) atomicAdd(&sums[1], (unsigned long long)s_cnt[1]);
+            if (s_cnt[2]) atomicAdd(&sums[2], (unsigned long long)s_cnt[2]);
+        }
     }
 }
 
@@ -149,12 +155,12 @@ __global__ void __launch_bounds__(256) k_er_finalize(const int32_t* __restrict__
 
 cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int K,
                                  float threshold, int32_t* triples, unsigned long long* tpfpfn,
-                                 cudaStream_t stream) {
+                                 unsigned long long* sums, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const int W = (T + 31) >> 5;
     const size_t smem = size_t(3) * K * W * sizeof(uint32_t);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    k_metric_counts<<<B, 128, smem, stream>>>(y_true, y_pred, T, K, threshold, triples, tpfpfn);
+    k_metric_counts<<<B, 128, smem, stream>>>(y_true, y_pred, T, K, threshold, triples, tpfpfn, sums);
     return cudaGetLastError();
 }
 

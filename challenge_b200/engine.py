@@ -222,20 +222,29 @@ class Engine:
                                    self._ptr(out), self._stream()))
         return out
 
-    def metric_counts(self, y_true, y_pred, threshold=0.5, tpfpfn=None, want_er=True):
-        """-> (triples [B,3] int32, tpfpfn [3] int64 accumulated, er [B] float or None)."""
+    def metric_counts(self, y_true, y_pred, threshold=0.5, tpfpfn=None, want_er=True, counts=None):
+        """-> (triples [B,3] int32, tpfpfn [3] int64 accumulated, er [B] float or None).
+
+        ``counts``: optional int64 ``[6]`` device tensor ``[TP, FP, FN, sum n_true, sum n_pred,
+        sum correct]`` accumulated in place (the multi-GPU all-reduce payload); it then also
+        serves as ``tpfpfn``."""
         torch = _torch()
         yt = torch.as_tensor(y_true, dtype=torch.float32, device=self.device).contiguous()
         yp = torch.as_tensor(y_pred, dtype=torch.float32, device=self.device).contiguous()
         B, T, K = yt.shape
         assert yp.shape == yt.shape
         triples = self._empty((B, 3), torch.int32)
-        if tpfpfn is None:
+        sums = None
+        if counts is not None:
+            assert counts.dtype == torch.int64 and counts.numel() == 6 and counts.is_contiguous()
+            tpfpfn, sums = counts[:3], counts[3:]
+        elif tpfpfn is None:
             tpfpfn = torch.zeros(3, dtype=torch.int64, device=self.device)
         er = self._empty((B,)) if want_er else None
         L.check(self.lib.iris_metric_counts(self._ctx, self._ptr(yt), self._ptr(yp), B, T, K,
                                             float(threshold), self._ptr(triples),
-                                            self._ptr(tpfpfn), self._ptr(er), self._stream()))
+                                            self._ptr(tpfpfn), self._ptr(sums), self._ptr(er),
+                                            self._stream()))
         return triples, tpfpfn, er
 
 

@@ -130,10 +130,12 @@ int iris_stft(iris_ctx* ctx, const float* wav, int n_chan, int64_t n_samples, in
  * micro counts (metrics.py:290-298) for y_true, y_pred [B,T,K] device floats.
  *   d_triples : [B,3] int32  (n_true, n_pred, correct)
  *   d_tpfpfn  : [3]   uint64 ACCUMULATED (the reference's F1 metric is never reset), or NULL
+ *   d_sums    : [3]   uint64 ACCUMULATED batch totals of the triples (together with d_tpfpfn
+ *                     the payload of the multi-GPU count all-reduce), or NULL
  *   d_er      : [B]   float  score per sample (metrics.py:268-273), or NULL */
 int iris_metric_counts(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred, int batch,
                        int n_frame, int n_classes, float threshold, int32_t* d_triples,
-                       uint64_t* d_tpfpfn, float* d_er, iris_stream stream);
+                       uint64_t* d_tpfpfn, uint64_t* d_sums, float* d_er, iris_stream stream);
 
 /* Algorithmic HBM bytes of the last uploaded plan for `mode`: 4 * (samples of
  * every kept source frame range read + output elements); used by bench.py's roofline. */
