@@ -55,7 +55,30 @@ SIGNATURES = {
     'iris_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i32p, C.c_int]),
     'iris_plan_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
+    # stand-alone stages (include/iris.h, second half)
+    'iris_op_mask': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                               C.c_void_p, C.c_int, C.c_void_p]),
+    'iris_op_stft_filter': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_int, C.c_void_p]),
+    'iris_op_random_shift': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    'iris_op_pointwise': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                    C.c_int, C.c_float, C.c_void_p]),
+    'iris_op_chan_map': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    'iris_op_mel': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p]),
+    'iris_op_minmax': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_int, C.c_void_p]),
+    'iris_op_sum_voices': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                     C.c_int64, C.c_void_p]),
+    'iris_op_avg_pool_time': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'iris_op_cos_sim': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p]),
 }
+PW_C2MP, PW_MP2C, PW_LOG_MAGPHASE, PW_LOG_ON_MEL, PW_MULTIPLY = range(5)
+MAP_MONO_CHAN, MAP_STEREO_MONO, MAP_MERGE_AUG = range(3)
 
 _lib = None
 
@@ -70,20 +93,12 @@ def load():
             'challenge_b200/libiris.so is missing -- build it with '
             '`python -m challenge_b200.build` (needs nvcc).  There is no CPU fallback.')
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(SIGNATURES.items()) + list(_ops_signatures().items()):
+    for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
     _lib = lib
     return lib
-
-
-def _ops_signatures():
-    try:
-        from ._ops_sig import OPS_SIGNATURES
-        return OPS_SIGNATURES
-    except ImportError:
-        return {}
 
 
 def check(rc):

@@ -8,106 +8,18 @@
 #include <string>
 #include <vector>
 
-#include "../../include/iris.h"
-#include "iris_common.cuh"
-#include "iris_launch.h"
+#include "iris_ctx.h"
 
 using namespace iris;
 
-namespace {
-
 thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) {
-    g_err = msg;
-    return code;
+namespace iris {
+std::string& last_error() { return g_err; }
 }
-int cuda_fail(cudaError_t e, const char* what) {
-    g_err = std::string(what) + ": " + cudaGetErrorString(e);
-    return IRIS_ERR_CUDA;
-}
-#define CU(x)                                         \
-    do {                                              \
-        cudaError_t e_ = (x);                         \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T>
-    T* as() const { return static_cast<T*>(p); }
-};
-
-struct Bank {
-    bool ready = false;
-    int n_items = 0, n_chan = 0, n_classes = 0;
-    std::vector<int64_t> offsets;      // samples per channel, cumulative
-    std::vector<int64_t> pad_offsets;  // padded floats per channel, cumulative
-    std::vector<int32_t> n_frames;
-    int max_frames = 0;
-    DevBuf padded, activity, labels, d_n_frames;
-    std::vector<uint8_t> h_activity;   // host mirror (voice bank)
-};
-
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-}  // namespace
-
-struct iris_ctx {
-    int device = 0;
-    int num_sms = 148;
-    Bank banks[3];
-    DevBuf tw, whalf;
-    // mel (CSR by mel bin)
-    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_taps = 0;
-    int mel_L[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    DevBuf mel_info, mel_w;
-    // plan
-    bool has_plan = false, labels_done = false;
-    int B = 0, T = 0, V = 0, M = 0, C = 0;
-    int n_tmask = 0, n_fmask = 0, filter_k = 0, remap = 0, c_out = 0;
-    std::vector<Seg> h_segs;
-    std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
-    std::vector<int32_t> h_seg_ptr;
-    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
-    DevBuf tiles, sched;
-    int max_segs = 1;
-    void* h_stage = nullptr;  // pinned staging for the plan blob
-    size_t h_stage_cap = 0;
-    cudaEvent_t stage_free = nullptr;
-    // device views into plan_blob
-    Seg* d_segs = nullptr;
-    int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
-            *d_voice_shift = nullptr, *d_tmask = nullptr, *d_fmask = nullptr;
-    float *d_merge_f = nullptr, *d_merge_sf = nullptr;
-    // roofline measurement hook
-    bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-    size_t prof_used = 0;
-};
 
 namespace {
 
-int set_device(iris_ctx* c) {
-    CU(cudaSetDevice(c->device));
-    return IRIS_OK;
-}
+int set_device(iris_ctx* c) { return iris_set_device(c); }
 
 int build_tables(iris_ctx* c) {
     // inter-pass twiddles W512^(n2*k1), two k1 per float4: [m][n2] = {k1 = 2m, k1 = 2m + 1}
@@ -229,6 +141,11 @@ int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
 
 }  // namespace
 
+int iris_set_device(iris_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return IRIS_OK;
+}
+
 extern "C" {
 
 int iris_abi_version(void) { return IRIS_ABI_VERSION; }
@@ -276,7 +193,8 @@ int iris_ctx_destroy(iris_ctx* c) {
         b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
     }
     for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
-                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->sched})
+                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->sched,
+                      &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stage_free) cudaEventDestroy(c->stage_free);
@@ -317,10 +235,21 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     for (int r = 0; r < 8; ++r) taps += L[r];
     bool long_filter = false;
     for (int r = 0; r < 8; ++r) long_filter = long_filter || L[r] > 12;
-    if (f_n > fused_max_mel_window() || taps > fused_max_mel_taps() || long_filter)
-        return fail(IRIS_ERR_UNSUPPORTED,
-                    "mel matrix spans more than 136 bins or has a filter wider than 12 bins; use "
-                    "the unfused mel projection");
+    // the stand-alone projection (iris_op_mel) takes any matrix: dense weights + column supports
+    {
+        std::vector<int32_t> lo32(n_mel), len32(n_mel);
+        for (int m = 0; m < n_mel; ++m) { lo32[m] = lo_of[m] < 0 ? 0 : lo_of[m]; len32[m] = len_of[m]; }
+        CU(c->mel_dense.reserve(size_t(n_bins) * n_mel * 4));
+        CU(c->mel_lo.reserve(size_t(n_mel) * 4));
+        CU(c->mel_len.reserve(size_t(n_mel) * 4));
+        CU(cudaMemcpy(c->mel_dense.p, w, size_t(n_bins) * n_mel * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->mel_lo.p, lo32.data(), size_t(n_mel) * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->mel_len.p, len32.data(), size_t(n_mel) * 4, cudaMemcpyHostToDevice));
+        c->mel_bins = n_bins;
+        c->n_mel = n_mel;
+    }
+    c->mel_fusable = !(f_n > fused_max_mel_window() || taps > fused_max_mel_taps() || long_filter);
+    if (!c->mel_fusable) return IRIS_OK;   // iris_features(mel modes) then reports UNSUPPORTED
     std::vector<uint32_t> info(n_mel, 0);
     std::vector<float> fw(size_t(std::max(taps, 1)) * 16, 0.f);
     int row0 = 0;
@@ -705,6 +634,10 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     }
     const bool mel = mode >= IRIS_FEAT_MEL;
     if (mel && c->n_mel == 0) return fail(IRIS_ERR_STATE, "iris_set_mel not called");
+    if (mel && !c->mel_fusable)
+        return fail(IRIS_ERR_UNSUPPORTED,
+                    "mel matrix spans more than 136 bins or has a filter wider than 12 bins: run "
+                    "IRIS_FEAT_MAGPHASE + iris_op_mel instead of the fused mel epilogue");
     if (mel && c->remap != IRIS_REMAP_NONE)
         return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
     FusedParams p;

@@ -1,0 +1,109 @@
+// Internal state of libiris shared by the extern "C" translation units (not a public header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/iris.h"
+#include "iris_common.cuh"
+#include "iris_launch.h"
+
+namespace iris {
+
+std::string& last_error();   // thread-local text behind iris_last_error()
+
+inline int fail(int code, const std::string& msg) {
+    last_error() = msg;
+    return code;
+}
+inline int cuda_fail(cudaError_t e, const char* what) {
+    last_error() = std::string(what) + ": " + cudaGetErrorString(e);
+    return IRIS_ERR_CUDA;
+}
+#define CU(x)                                               \
+    do {                                                    \
+        cudaError_t e_ = (x);                               \
+        if (e_ != cudaSuccess) return ::iris::cuda_fail(e_, #x); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct Bank {
+    bool ready = false;
+    int n_items = 0, n_chan = 0, n_classes = 0;
+    std::vector<int64_t> offsets;      // samples per channel, cumulative
+    std::vector<int64_t> pad_offsets;  // padded floats per channel, cumulative
+    std::vector<int32_t> n_frames;
+    int max_frames = 0;
+    DevBuf padded, activity, labels, d_n_frames;
+    std::vector<uint8_t> h_activity;   // host mirror (voice bank)
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace iris
+
+struct iris_ctx {
+    using DevBuf = iris::DevBuf;
+    using Bank = iris::Bank;
+    using Seg = iris::Seg;
+    int device = 0;
+    int num_sms = 148;
+    Bank banks[3];
+    DevBuf tw, whalf;
+    // mel (CSR by mel bin)
+    int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_taps = 0;
+    int mel_L[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    DevBuf mel_info, mel_w;
+    // plan
+    bool has_plan = false, labels_done = false;
+    int B = 0, T = 0, V = 0, M = 0, C = 0;
+    int n_tmask = 0, n_fmask = 0, filter_k = 0, remap = 0, c_out = 0;
+    std::vector<Seg> h_segs;
+    std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
+    std::vector<int32_t> h_seg_ptr;
+    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
+    DevBuf tiles, sched;
+    int max_segs = 1;
+    void* h_stage = nullptr;  // pinned staging for the plan blob
+    size_t h_stage_cap = 0;
+    cudaEvent_t stage_free = nullptr;
+    // device views into plan_blob
+    Seg* d_segs = nullptr;
+    int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
+            *d_voice_shift = nullptr, *d_tmask = nullptr, *d_fmask = nullptr;
+    float *d_merge_f = nullptr, *d_merge_sf = nullptr;
+    // roofline measurement hook
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    // stand-alone ops (iris_ops_abi.cu): dense mel matrix + column supports, small scratch
+    DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops;
+    int mel_bins = 0;
+    bool mel_fusable = false;
+};
+
+int iris_set_device(iris_ctx* c);

@@ -45,4 +45,25 @@ cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B
                                  unsigned long long* sums, cudaStream_t stream);
 cudaError_t launch_er_finalize(const int32_t* triples, int B, float* er, cudaStream_t stream);
 
+// k_ops.cu -- stand-alone stages (un-fused forms of the fused epilogue + label / metric helpers)
+cudaError_t launch_axis_scale(const float* x, const float* m, float* out, size_t outer, size_t n_axis,
+                              size_t inner, cudaStream_t st);
+cudaError_t launch_axis_shift(const float* x, float* out, size_t outer, size_t n_axis, size_t inner,
+                              int delta, cudaStream_t st);
+cudaError_t launch_pointwise(int op, const float* x, float* out, size_t rows, int C, int width,
+                             int n_log, float scalar, cudaStream_t st);
+cudaError_t launch_chan_map(const float* x, float* out, size_t rows, int w_in, int w_out,
+                            const int32_t* idx, const float* coef, size_t rows_per_sample,
+                            cudaStream_t st);
+cudaError_t launch_mel_project(const float* x, const float* W, const int32_t* lo, const int32_t* len,
+                               float* out, int B, int F, int T, int C, int n_mel, cudaStream_t st);
+cudaError_t launch_minmax(const float* x, float* out, uint32_t* mm, size_t S, size_t per_sample, int w,
+                          int split, int variant, cudaStream_t st);
+cudaError_t launch_sum_axis(const float* y, float* out, size_t outer, int V, size_t inner,
+                            cudaStream_t st);
+cudaError_t launch_avg_pool_time(const float* y, float* out, int B, int T, int K, int r, int out_len,
+                                 int pad_left, int binarize, cudaStream_t st);
+cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out, int B, int T, int K,
+                           cudaStream_t st);
+
 }  // namespace iris

@@ -50,6 +50,7 @@ class Engine:
         self._ctx = C.c_void_p()
         L.check(self.lib.iris_ctx_create(int(device), C.byref(self._ctx)))
         self.n_mel = 0
+        self.mel_matrix = None
         self.bank_frames = {}
         self.bank_chan = None
         self.n_classes = 0

@@ -1,0 +1,227 @@
+"""Drop-in mirror of the reference's ``pipeline.py``: ``make_pipeline`` / ``merge_complex_specs``.
+
+The reference zips three shuffled ``tf.data`` streams of PRE-COMPUTED complex spectrograms and
+maps ``merge_complex_specs`` over them, one sample at a time on one host thread
+(pipeline.py:113-175).  Here the banks are WAVEFORMS (``[chan, samples]``; the STFT of
+``data_utils.load_wav`` moved into the per-step GPU path) registered once in HBM; the host
+only draws the randomness of a whole batch in the reference's draw order
+(``plan.draw_batch``) and the fused kernel produces ``batch`` samples per launch.
+
+``make_pipeline`` returns an :class:`IrisDataset` with the slice of the ``tf.data`` surface
+that ``sj_train.make_dataset`` (sj_train.py:92-130) uses -- ``map``, ``batch``, ``prefetch``,
+``take``, ``repeat``, iteration.  Chaining the drop-in functions in sj_train's order
+(``to_frame_labels``, ``augment``, ``stereo_mono`` | ``random_merge_aug(n)``,
+``stft_filter(k)``, ``batch``, ``complex_to_magphase``, ``magphase_to_mel(n)``, ``minmax``,
+``log_on_mel``) is recognised and lowered to ONE fused launch per batch; any other callable
+runs after it on the un-fused tensors (the stand-alone kernels), so arbitrary chains work.
+"""
+import numpy as np
+
+from . import _lib as L
+from . import _ops as O
+from .engine import get_engine
+from .plan import ShuffleStream, draw_batch
+
+AUTOTUNE = -1   # tf.data.experimental.AUTOTUNE stand-in for .prefetch()
+
+
+def _is_waveform_bank(items):
+    return np.asarray(items[0]).ndim == 2
+
+
+class IrisDataset:
+    """Lazy description of ``make_pipeline(...)`` followed by ``map`` / ``batch`` stages."""
+
+    def __init__(self, source, stages=(), batch_size=None, limit=None):
+        self._src = source
+        self._stages = tuple(stages)        # callables; ('batch', n) marks the batch point
+        self._batch = batch_size
+        self._limit = limit
+
+    # ---- tf.data surface used by sj_train.make_dataset ----
+    def map(self, fn, num_parallel_calls=None):
+        return IrisDataset(self._src, self._stages + (fn,), self._batch, self._limit)
+
+    def batch(self, batch_size, drop_remainder=False):
+        if self._batch is not None:
+            raise ValueError('IrisDataset is already batched')
+        return IrisDataset(self._src, self._stages + (('batch', int(batch_size)),),
+                           int(batch_size), self._limit)
+
+    def prefetch(self, buffer_size=None):
+        return self
+
+    def repeat(self, count=None):
+        return self
+
+    def shuffle(self, buffer_size, **kwargs):
+        return self      # the source streams are already shuffled (pipeline.py:147,154,164)
+
+    def take(self, count):
+        return IrisDataset(self._src, self._stages, self._batch, int(count))
+
+    # ---- lowering ----
+    def _lower(self):
+        """Split the stage list into what the fused kernel absorbs and the remainder."""
+        fused = dict(frame_labels=False, augment=False, remap=L.REMAP_NONE, n_out=0, filt=0,
+                     mode=L.FEAT_COMPLEX, n_mels=0, mel_matrix=None)
+        rest = []
+        state = 'pre'       # pre-batch element stages -> post-batch feature stages
+        order = {'to_frame_labels': 0, 'augment': 1, 'stereo_mono': 2, 'merge_aug': 2,
+                 'stft_filter': 3}
+        last = -1
+        stages = list(self._stages)
+        i = 0
+        while i < len(stages):
+            st = stages[i]
+            tag = getattr(st, '_iris_stage', None) if callable(st) else st
+            if rest:
+                rest.append(st)
+            elif state == 'pre' and tag and tag[0] in order and order[tag[0]] > last:
+                last = order[tag[0]]
+                if tag[0] == 'to_frame_labels':
+                    fused['frame_labels'] = True
+                elif tag[0] == 'augment':
+                    fused['augment'] = True
+                elif tag[0] == 'stereo_mono':
+                    fused['remap'], fused['n_out'] = L.REMAP_STEREO_MONO, 3
+                elif tag[0] == 'merge_aug':
+                    fused['remap'], fused['n_out'] = L.REMAP_MERGE_AUG, int(tag[1])
+                elif tag[0] == 'stft_filter':
+                    fused['filt'] = int(tag[1])
+            elif state == 'pre' and tag and tag[0] == 'batch':
+                state = 'post'
+            elif state == 'post' and tag and tag[0] == 'magphase' and fused['mode'] == L.FEAT_COMPLEX:
+                fused['mode'] = L.FEAT_MAGPHASE
+            elif state == 'post' and tag and tag[0] == 'mel' and fused['mode'] == L.FEAT_MAGPHASE \
+                    and fused['remap'] == L.REMAP_NONE:
+                fused['mode'], fused['n_mels'], fused['mel_matrix'] = L.FEAT_MEL, tag[1], tag[2]
+            elif state == 'post' and tag and tag[0] == 'minmax' and fused['mode'] == L.FEAT_MEL \
+                    and i + 1 < len(stages) and getattr(stages[i + 1], '_iris_stage', (None,))[0] == 'log_on_mel':
+                fused['mode'] = L.FEAT_LOGMEL_MINMAX
+                i += 1
+            elif state == 'post' and tag and tag[0] == 'log_on_mel' and fused['mode'] == L.FEAT_MEL:
+                fused['mode'] = L.FEAT_LOGMEL
+            else:
+                rest.append(st)
+            i += 1
+        return fused, rest
+
+    def __iter__(self):
+        src = self._src
+        eng = src['engine']
+        fused, rest = self._lower()
+        B = self._batch or 1
+        n = 0
+        while self._limit is None or n < self._limit:
+            d = draw_batch(O.rng(), B, src['n_frame'], src['bg_frames'], src['voice_frames'],
+                           src['noise_frames'], max_voices=src['max_voices'],
+                           max_noises=src['max_noises'], snr=src['snr'], min_ratio=src['min_ratio'],
+                           min_noise_ratio=src['min_noise_ratio'],
+                           n_time_masks=6 if fused['augment'] else 0, time_mask_max=24,
+                           n_freq_masks=1 if fused['augment'] else 0, freq_mask_max=16,
+                           merge_extra=max(fused['n_out'] - 2, 0) if fused['remap'] == L.REMAP_MERGE_AUG else 0,
+                           streams=src['streams'])
+            if fused['mode'] >= L.FEAT_MEL:
+                cur = eng.mel_matrix
+                if cur is None or cur.shape != fused['mel_matrix'].shape \
+                        or not np.array_equal(cur, fused['mel_matrix']):
+                    eng.set_mel(mel_matrix=fused['mel_matrix'])
+            eng.upload_plan(d, stft_filter=fused['filt'], chan_remap=fused['remap'],
+                            n_out_chan=fused['n_out'])
+            frame, vtk, _ = eng.labels(want_vtk=not fused['frame_labels'], want_keep=False)
+            x = eng.features(fused['mode'])
+            y = frame if fused['frame_labels'] else vtk
+            if self._batch is None:
+                x, y = x[0], y[0]
+            batched = self._batch is not None
+            for st in rest:
+                if isinstance(st, tuple) and st[0] == 'batch':
+                    batched = True          # elements were produced batched already
+                    continue
+                res = st(x, y)
+                x, y = res if isinstance(res, tuple) else (res, y)
+            n += 1
+            yield x, y
+
+
+def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300, n_classes=3,
+                        t_axis=1, min_ratio=2 / 3, min_noise_ratio=1 / 2, snr=-20,
+                        seperate_noise_voice=False, *, draws=None):
+    '''
+    pipeline.py:6-110 for ONE sample given as waveforms: ``background`` [chan, samples],
+    ``voices_and_labels`` = (list of [chan, samples] voices -- the whole padded_batch group --,
+    labels [n, n_classes]), ``noises`` = list of [chan, samples] or None.
+
+    OUTPUT:
+        complex_spec: (freq, time, chan2)
+        labels: (n_voices, time, n_classes)
+    '''
+    if seperate_noise_voice:
+        raise NotImplementedError("seperate_noise_voice ('se' model outputs, pipeline.py:37-38) is "
+                                  'outside the hot path (SURVEY.md 8f rank 4)')
+    voices, labels = voices_and_labels
+    if np.asarray(background).ndim != 2:
+        raise NotImplementedError(
+            'merge_complex_specs takes waveforms [chan, samples]; mixing pre-computed '
+            'spectrogram banks is the reference\'s offline format (SURVEY.md 8f rank 2)')
+    eng = get_engine()
+    bf = eng.register_bank(L.BANK_BG, [background])
+    vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
+    nf = eng.register_bank(L.BANK_NOISE, list(noises)) if noises is not None else None
+    V, M = len(voices), (len(noises) if noises is not None else 0)
+    if draws is None:
+        draws = draw_batch(O.rng(), 1, n_frame, bf, vf, nf, max_voices=V, max_noises=M, snr=snr,
+                           min_ratio=min_ratio, min_noise_ratio=min_noise_ratio)
+        draws.voice_id[:] = np.arange(V)
+        if M:
+            draws.noise_id[:] = np.arange(M)
+    eng.upload_plan(draws)
+    _, vtk, _ = eng.labels(want_vtk=True, want_keep=False)
+    spec = eng.features(L.FEAT_COMPLEX)
+    return spec[0], vtk[0]
+
+
+def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan, samples])
+                  voices,       # a list of human voices
+                  labels,       # a list of labels of human voices
+                  noises=None,  # a list of additional noises
+                  n_frame=300,  # number of frames per sample
+                  max_voices=10,
+                  max_noises=10,
+                  n_classes=3,
+                  **kwargs):
+    '''
+    OUTPUT
+        dataset: IrisDataset yielding
+                 complex spectrogram: [freq_bins, n_frame, chan*2]
+                     [..., :chan] = real
+                     [..., chan:] = imag
+                 labels: [max_voices, n_frame, n_classes]
+    (pipeline.py:113-175; kwargs = merge_complex_specs' min_ratio / min_noise_ratio / snr)
+    '''
+    if not _is_waveform_bank(backgrounds):
+        # the reference's check (pipeline.py:136) is for 3-D spectrograms; this build starts
+        # from the waveforms those spectrograms were made of
+        raise NotImplementedError(
+            'make_pipeline takes banks of waveforms [chan, samples]: the STFT of load_wav runs '
+            'inside the fused kernel.  Pre-computed spectrogram banks are the reference\'s offline '
+            'format (SURVEY.md 8f rank 2)')
+    assert len(voices) == len(labels)
+    assert len(np.asarray(labels[0]).shape) == 1 and np.asarray(labels[0]).shape[0] == n_classes, \
+        'labels must be in the form of [n_samples, n_classes]'
+    if kwargs.get('seperate_noise_voice'):
+        raise NotImplementedError("seperate_noise_voice is outside the hot path (SURVEY.md 8f rank 4)")
+    eng = get_engine()
+    bf = eng.register_bank(L.BANK_BG, list(backgrounds))
+    vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
+    nf = eng.register_bank(L.BANK_NOISE, list(noises)) if noises is not None else None
+    r = O.rng()
+    streams = {'bg': ShuffleStream(len(backgrounds), r), 'voice': ShuffleStream(len(voices), r)}
+    if noises is not None:
+        streams['noise'] = ShuffleStream(len(noises), r)
+    source = dict(engine=eng, n_frame=int(n_frame), bg_frames=bf, voice_frames=vf, noise_frames=nf,
+                  max_voices=int(max_voices), max_noises=int(max_noises) if noises is not None else 0,
+                  snr=kwargs.get('snr', -20), min_ratio=kwargs.get('min_ratio', 2 / 3),
+                  min_noise_ratio=kwargs.get('min_noise_ratio', 1 / 2), streams=streams)
+    return IrisDataset(source)

@@ -148,6 +148,66 @@ int iris_plan_bytes(iris_ctx* ctx, int mode, const uint8_t* host_keep, int64_t* 
 int iris_profile_enable(iris_ctx* ctx, int enable);
 int iris_profile_read(iris_ctx* ctx, double* total_ms, int32_t* n_launches, int reset);
 
+/* ---------------------------------------------------------------------------------------
+ * Stand-alone stages: the reference's public functions applied one at a time (what a
+ * tf.data `.map(fn)` of a single function binds to).  The fused iris_features() path above
+ * is the hot path; these are its stages un-fused, for callers that compose the reference's
+ * functions in an order the fused kernel does not cover.  x / out are DEVICE fp32 tensors,
+ * C-contiguous, out may alias x unless noted.  Small parameter arrays are HOST pointers.
+ * --------------------------------------------------------------------------------------- */
+
+/* transforms.mask (transforms.py:12-40): x viewed as [outer, n_axis, inner]; masks = n_mask
+ * host pairs (size, offset) in draw order (transforms.py:25-26); out = x * mask (product,
+ * signed zeros kept).  Also data_utils.augment (data_utils.py:58-61) = two calls. */
+int iris_op_mask(iris_ctx* ctx, const float* d_x, float* d_out, int64_t outer, int64_t n_axis,
+                 int64_t inner, const int32_t* masks, int n_mask, iris_stream stream);
+/* data_utils.stft_filter(k) (data_utils.py:126-136): x [n_bins, inner], bins 1..k times 0. */
+int iris_op_stft_filter(iris_ctx* ctx, const float* d_x, float* d_out, int64_t n_bins,
+                        int64_t inner, int k, iris_stream stream);
+/* transforms.random_shift (transforms.py:43-47): zero-pad `width` both sides of the axis and
+ * crop at `offset` in [0, 2*width].  out must NOT alias x. */
+int iris_op_random_shift(iris_ctx* ctx, const float* d_x, float* d_out, int64_t outer,
+                         int64_t n_axis, int64_t inner, int width, int offset, iris_stream stream);
+/* Row-wise stages on [rows, 2*n_chan] (first half real / magnitude, second imag / phase). */
+enum {
+    IRIS_PW_COMPLEX_TO_MAGPHASE = 0, /* transforms.py:111-123 */
+    IRIS_PW_MAGPHASE_TO_COMPLEX = 1, /* transforms.py:126-134 */
+    IRIS_PW_LOG_MAGPHASE = 2,        /* transforms.py:80-86; `param_i` = n_chan argument      */
+    IRIS_PW_LOG_ON_MEL = 3,          /* data_utils.py:50-55; any shape, pass width = 1        */
+    IRIS_PW_MULTIPLY = 4             /* data_utils.py:120-123; `param_f` = multiply_factor    */
+};
+int iris_op_pointwise(iris_ctx* ctx, int op, const float* d_x, float* d_out, int64_t rows,
+                      int width, int param_i, float param_f, iris_stream stream);
+/* Channel remaps on [rows, w_in] -> [rows, w_out] (out must NOT alias x):
+ *   mono_chan (data_utils.py:73-76; w_out = w_in - 1, the reference's broadcast quirk),
+ *   stereo_mono (79-82; 4 -> 6), random_merge_aug(number) (100-117; 4 -> 2*number, `factor`
+ *   = host [n_samples, number-2] draws of U(0.1, 0.9), rows_per_sample rows per sample). */
+enum { IRIS_MAP_MONO_CHAN = 0, IRIS_MAP_STEREO_MONO = 1, IRIS_MAP_MERGE_AUG = 2 };
+int iris_op_chan_map(iris_ctx* ctx, int kind, const float* d_x, float* d_out, int64_t rows,
+                     int w_in, int w_out, const float* factor, int64_t n_samples,
+                     int64_t rows_per_sample, iris_stream stream);
+/* transforms.magphase_to_mel (transforms.py:51-77) with the matrix of iris_set_mel (any
+ * matrix): x [B, n_bins, T, 2C] -> out [B, n_mel, T, C] (unbatched: B = 1). */
+int iris_op_mel(iris_ctx* ctx, const float* d_x, float* d_out, int B, int T, int n_chan,
+                iris_stream stream);
+/* data_utils.minmax (data_utils.py:37-47, safe_div utils.py:114-116): variant 0, one group;
+ * transforms.minmax_norm_magphase (transforms.py:89-107): variant 1, the two halves of the
+ * last axis (width) normalised separately.  x [n_samples, per_sample]. */
+int iris_op_minmax(iris_ctx* ctx, int variant, const float* d_x, float* d_out, int64_t n_samples,
+                   int64_t per_sample, int width, iris_stream stream);
+/* data_utils.to_frame_labels (data_utils.py:64-70): y [outer, V, inner] -> [outer, inner]. */
+int iris_op_sum_voices(iris_ctx* ctx, const float* d_y, float* d_out, int64_t outer, int V,
+                       int64_t inner, iris_stream stream);
+/* AveragePooling1D(r, r, 'same') over time of y [B, T, K] -> [B, ceil(T/r), K];
+ * binarize != 0 adds the `>= 0.5` of data_utils.label_downsample (data_utils.py:85-97; the
+ * `[:resolution]` batch slice is the caller's), binarize == 0 is the smoothing pool of
+ * metrics.er_score (metrics.py:222-224). */
+int iris_op_avg_pool_time(iris_ctx* ctx, const float* d_y, float* d_out, int B, int T, int K, int r,
+                          int binarize, iris_stream stream);
+/* metrics.cos_sim (metrics.py:277-287): y_true, y_pred [B, T, K<=8] -> out [B]. */
+int iris_op_cos_sim(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred, float* d_out,
+                    int B, int T, int K, iris_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

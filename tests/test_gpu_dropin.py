@@ -1,0 +1,282 @@
+"""GPU tests of the drop-in modules (challenge_b200.{pipeline,transforms,data_utils,metrics}):
+the reference's own unit tests restated against the same function names (known answers in
+tests/golden/reference_kats.json, transcribed from transforms_test.py / metrics_test.py /
+pipeline_test.py), plus parity of every stand-alone stage with the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import nmax_err, phase_err
+
+pytestmark = pytest.mark.gpu
+
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_kats.json')))
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def mods(engine):
+    import challenge_b200
+    from challenge_b200 import data_utils, engine as E, metrics, pipeline, transforms
+    E._engines[0] = engine          # share the session engine
+    challenge_b200.set_seed(0)
+    return pipeline, transforms, data_utils, metrics
+
+
+# ---- transforms_test.py ----
+def test_mask(mods):
+    _, TR, _, _ = mods
+    for key in ('mask_axis0', 'mask_axis1'):
+        k = KATS[key]
+        got = TR.mask(np.array(k['org'], np.float32), axis=k['axis'],
+                      max_mask_size=k['max_mask_size'], n_mask=k['n_mask'], draws=k['draws'])
+        assert np.array_equal(_np(got), np.array(k['target'], np.float32))
+    # random draws stay inside the reference's ranges and zero whole rows
+    x = np.random.default_rng(0).standard_normal((257, 100, 4)).astype(np.float32)
+    got = _np(TR.mask(x, axis=-2, max_mask_size=24, n_mask=6))
+    cols = ~got.any(axis=(0, 2))
+    assert cols.sum() < 6 * 24 and np.array_equal(got[:, ~cols], x[:, ~cols])
+
+
+def test_random_shift(mods):
+    _, TR, _, _ = mods
+    k = KATS['random_shift']
+    got = TR.random_shift(np.array(k['org'], np.float32), axis=k['axis'], width=k['width'],
+                          offset=k['offset'])
+    assert np.array_equal(_np(got), np.array(k['target'], np.float32))
+    assert _np(TR.random_shift(np.ones((5, 3), np.float32), axis=1, width=2)).shape == (5, 3)
+
+
+def test_magphase_to_mel(mods):
+    from oracle import transforms as OT
+    _, TR, _, _ = mods
+    rng = np.random.default_rng(1)
+    x = rng.random((4, 257, 100, 4), dtype=np.float32)
+    got = _np(TR.magphase_to_mel(80)(x))
+    assert got.shape == (4, 80, 100, 2)                       # transforms_test.py:45-55
+    assert nmax_err(got, OT.magphase_to_mel(80)(x)) < 1e-5
+    got = _np(TR.magphase_to_mel(80)(x[0]))
+    assert got.shape == (80, 100, 2)
+    assert nmax_err(got, OT.magphase_to_mel(80)(x[0])) < 1e-5
+    # a matrix the fused epilogue does not take (wide filters) still projects
+    got = _np(TR.magphase_to_mel(20, lower_edge_hertz=0.0, upper_edge_hertz=8000.0)(x))
+    ref = OT.magphase_to_mel(20, lower_edge_hertz=0.0, upper_edge_hertz=8000.0)(x)
+    assert nmax_err(got, ref) < 1e-5
+    with pytest.raises(ValueError):
+        TR.magphase_to_mel(80)(x[0, :, 0])
+
+
+def test_log_magphase(mods):
+    _, TR, _, _ = mods
+    k = KATS['log_magphase']
+    got = _np(TR.log_magphase(np.array(k['specs'], np.float32), n_chan=k['n_chan']))
+    np.testing.assert_allclose(got, np.array(k['target'], np.float32), rtol=0, atol=1e-6)
+
+
+def test_minmax_norm_magphase(mods):
+    from oracle import transforms as OT
+    _, TR, _, _ = mods
+    x = np.random.default_rng(2).standard_normal((5, 257, 30, 4)).astype(np.float32) * 7
+    got = _np(TR.minmax_norm_magphase(x))
+    for half in (got[..., :2], got[..., 2:]):                  # transforms_test.py:64-77
+        assert np.allclose(half.reshape(5, -1).min(1), 0) and np.allclose(half.reshape(5, -1).max(1), 1, atol=1e-6)
+    assert nmax_err(got, OT.minmax_norm_magphase(x)) < 1e-6
+
+
+def test_complex_to_magphase_and_back(mods):
+    _, TR, _, _ = mods
+    k = KATS['complex_to_magphase']
+    c = np.array(k['complex'], np.float32)
+    mp = _np(TR.complex_to_magphase(c))
+    np.testing.assert_allclose(mp, np.array(k['magphase'], np.float32), rtol=0, atol=1e-6)
+    back = _np(TR.magphase_to_complex(np.array(k['magphase'], np.float32)))
+    np.testing.assert_allclose(back, c, rtol=0, atol=1e-6)     # transforms_test.py:89-96
+    x = np.random.default_rng(3).standard_normal((3, 257, 50, 8)).astype(np.float32)
+    from oracle import transforms as OT
+    got, ref = _np(TR.complex_to_magphase(x)), OT.complex_to_magphase(x)
+    assert nmax_err(got[..., :4], ref[..., :4]) < 1e-6
+    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-5
+    x2, y = TR.complex_to_magphase(x, 'labels')
+    assert y == 'labels'
+
+
+def test_phase_vocoder_identity(mods):
+    _, TR, _, _ = mods
+    x = np.ones((257, 100, 6), np.float32)
+    assert TR.phase_vocoder(x, rate=1.) is x                    # transforms_test.py:98-101
+
+
+# ---- data_utils ----
+def test_load_wav_and_feature_chain(mods):
+    """metrics.evaluate's input side (metrics.py:41-54) on an in-memory waveform, incl. the
+    per-mel-row min-max quirk of the unbatched call."""
+    from oracle import data_utils as OD, transforms as OT
+    _, TR, D, _ = mods
+    wav = (np.random.default_rng(4).standard_normal((2, 48000)) * 0.1).astype(np.float32)
+    spec = D.load_wav(wav)
+    ref = OD.load_wav_array(wav)
+    assert nmax_err(_np(spec), ref) < 1e-4
+    x = D.stft_filter(16)(spec)
+    x = TR.complex_to_magphase(x)
+    x = TR.magphase_to_mel(80)(x)
+    x = D.minmax(x)
+    x = D.log_on_mel(x)
+    r = OD.stft_filter(16)(ref)
+    r = OT.complex_to_magphase(r)
+    r = OT.magphase_to_mel(80)(r)
+    r = OD.log_on_mel(OD.minmax(r))
+    assert _np(x).shape == r.shape == (80, 188, 2)
+    assert nmax_err(_np(x), r) < 1e-4
+
+
+def test_minmax_log_labels_and_remaps(mods):
+    from oracle import data_utils as OD
+    _, _, D, _ = mods
+    rng = np.random.default_rng(5)
+    x = rng.random((6, 80, 50, 2), dtype=np.float32) * 3
+    assert nmax_err(_np(D.minmax(x)), OD.minmax(x)) < 1e-6
+    const = np.full((2, 4, 4), 2.5, np.float32)                 # max == min: safe_div path
+    assert np.array_equal(_np(D.minmax(const)), OD.minmax(const))
+    assert nmax_err(_np(D.log_on_mel(x)), OD.log_on_mel(x)) < 1e-6
+    y = (rng.random((3, 7, 40, 3)) < 0.2).astype(np.float32)
+    _, got = D.to_frame_labels(None, y)
+    assert np.array_equal(_np(got), OD.to_frame_labels(None, y)[1])
+    spec = rng.standard_normal((257, 20, 4)).astype(np.float32)
+    assert np.array_equal(_np(D.stereo_mono(spec)), OD.stereo_mono(spec))
+    got, lab = D.mono_chan(spec, 'y')
+    assert lab == 'y' and np.array_equal(_np(got), OD.mono_chan(spec, 'y')[0])
+    assert D.mono_chan(spec) is spec                            # no-op without labels (quirk)
+    f = np.array([0.3, 0.7], np.float32)
+    assert np.array_equal(_np(D.random_merge_aug(4)(spec, factor=f)),
+                          OD.random_merge_aug(4)(spec, factor=f))
+    assert _np(D.random_merge_aug(5)(spec)).shape == (257, 20, 10)
+    with pytest.raises(ValueError):
+        D.random_merge_aug(4)(np.zeros((257, 20, 8), np.float32))
+    assert np.array_equal(_np(D.stft_filter(3)(spec)), OD.stft_filter(3)(spec))
+    _, got = D.multiply_label(3.0)(None, y)
+    assert np.array_equal(_np(got), y * 3)
+    x2 = D.speech_enhancement_preprocess(spec)
+    assert _np(x2).shape == (256, 20, 2)
+    specs, labels = D.augment(spec, 'y')
+    assert labels == 'y' and _np(specs).shape == spec.shape
+
+
+@pytest.mark.parametrize('T,r', [(626, 32), (512, 32), (100, 7), (31, 32), (64, 32)])
+def test_label_downsample(mods, T, r):
+    from oracle import data_utils as OD
+    _, _, D, _ = mods
+    rng = np.random.default_rng(T)
+    y = (rng.random((40, T, 3)) < 0.5).astype(np.float32)
+    _, got = D.label_downsample(r)(None, y)
+    _, ref = OD.label_downsample(r)(None, y)
+    assert np.array_equal(_np(got), ref) and ref.shape[0] == min(40, r)
+    _, got = D.label_downsample(r)(None, (y, 'a', 'b'))
+    assert got[1:] == ('a', 'b') and np.array_equal(_np(got[0]), ref)
+
+
+# ---- metrics_test.py ----
+def test_er_score(mods):
+    _, _, _, MT = mods
+    k = KATS['er_score']
+    g = np.zeros([k['batch'], k['frames'], k['classes']], np.float32)
+    p = np.zeros_like(g)
+    for c, s, e in k['gt']:
+        g[:, s:e, c] = 1
+    for c, t in k['predict']:
+        p[:, t - 2:t + 2, c] = 1
+    er = MT.er_score(smoothing=False)(g, p)
+    assert float(_np(er).mean()) == np.float32(k['mean_er'])      # metrics_test.py:25
+    assert _np(MT.er_counts(g, p)).tolist() == [[5, 5, 2], [5, 5, 2]]
+
+
+def test_f1_and_cos_sim(mods):
+    from oracle import metrics as OM
+    _, _, _, MT = mods
+    rng = np.random.default_rng(6)
+    yt = (rng.random((16, 200, 3)) < 0.3).astype(np.float32)
+    yt[3] = 0                                                    # a sample with no class at all
+    yt[5, :, 1] = 0
+    yp = np.clip(yt + rng.normal(0, 0.35, yt.shape), 0, 1).astype(np.float32)
+    f1, ref = MT.f1_score(), OM.f1_score()
+    for _ in range(3):                                           # the state accumulates
+        assert f1(yt, yp) == ref(yt, yp)
+    assert f1((yt,), (yp,)) == ref((yt,), (yp,))
+    got = _np(MT.cos_sim(yt, yp))
+    np.testing.assert_allclose(got, OM.cos_sim(yt, yp), rtol=0, atol=2e-6)
+
+
+# ---- pipeline_test.py ----
+def _wave_banks(rng, n_bg, n_voice, n_noise, chan=2, n_classes=30):
+    mk = lambda lo, hi: (rng.standard_normal((chan, int(rng.integers(lo, hi)))) * 0.1).astype(np.float32)
+    bgs = [mk(2000, 6000) for _ in range(n_bg)]
+    voices = [mk(1500, 5000) for _ in range(n_voice)]
+    for v in voices[::2]:
+        v[:, -v.shape[1] // 4:] = 0                              # zero tails (pipeline_test.py:21-24)
+    labels = np.eye(n_classes, dtype=np.float32)[rng.integers(0, n_classes, n_voice)]
+    noises = [mk(1500, 5000) for _ in range(n_noise)]
+    return bgs, voices, labels, noises
+
+
+def test_merge_complex_specs(mods):
+    """pipeline_test.py:13-42: [257, n_frame, chan*2] and [n_voices, n_frame, n_classes];
+    values against the oracle on the same draws."""
+    from challenge_b200 import _lib as L
+    from challenge_b200.plan import draw_batch
+    from oracle import chain
+    P, _, _, _ = mods
+    rng = np.random.default_rng(7)
+    bgs, voices, labels, noises = _wave_banks(rng, 1, 4, 2)
+    spec, label = P.merge_complex_specs(bgs[0], (voices, labels), noises, n_frame=10, n_classes=30)
+    assert _np(spec).shape == (257, 10, 4) and _np(label).shape == (4, 10, 30)
+    eng = mods[1].get_engine()
+    frames = lambda ws: np.array([1 + w.shape[1] // 256 for w in ws], np.int32)
+    d = draw_batch(np.random.default_rng(8), 1, 10, frames(bgs), frames(voices), frames(noises),
+                   max_voices=4, max_noises=2)
+    d.voice_id[:] = np.arange(4)
+    d.noise_id[:] = np.arange(2)
+    spec, label = P.merge_complex_specs(bgs[0], (voices, labels), noises, n_frame=10, n_classes=30,
+                                        draws=d)
+    ob, ov, on = chain.OracleBank(bgs), chain.OracleBank(voices), chain.OracleBank(noises)
+    ref, ref_l = chain.synth_clip(ob, ov, labels, on, d, 0, n_classes=30)
+    assert nmax_err(_np(spec), ref) < 1e-4
+    assert np.array_equal(_np(label), ref_l)
+
+
+def test_make_pipeline_and_dataset_chain(mods):
+    """pipeline_test.py:44-74 shapes, then sj_train.make_dataset's chain (sj_train.py:107-123)
+    fused vs the same functions applied one by one on the un-fused output."""
+    import challenge_b200
+    P, TR, D, _ = mods
+    rng = np.random.default_rng(9)
+    bgs, voices, labels, noises = _wave_banks(rng, 30, 40, 50, n_classes=30)
+    ds = P.make_pipeline(bgs, voices, labels, noises, n_frame=30, max_voices=4, max_noises=4,
+                         n_classes=30)
+    for s, l in ds.take(2):
+        assert _np(s).shape == (257, 30, 4) and _np(l).shape == (4, 30, 30)
+    bgs, voices, labels, noises = _wave_banks(rng, 6, 20, 8, n_classes=3)
+
+    def build(fuse):
+        challenge_b200.set_seed(123)
+        ds = P.make_pipeline(bgs, voices, labels, noises, n_frame=40, max_voices=4, max_noises=2,
+                             n_classes=3, snr=-20, min_ratio=1)
+        ds = ds.map(D.to_frame_labels)
+        if fuse:
+            ds = ds.batch(5).map(TR.complex_to_magphase).map(TR.magphase_to_mel(80))
+            return ds.map(D.minmax).map(D.log_on_mel).prefetch(P.AUTOTUNE)
+        ident = lambda x, y: (x, y)                              # breaks the fusion
+        ds = ds.batch(5).map(ident).map(TR.complex_to_magphase).map(TR.magphase_to_mel(80))
+        return ds.map(D.minmax).map(D.log_on_mel)
+
+    fused, rest = build(True)._lower()
+    assert rest == []
+    assert len(build(False)._lower()[1]) == 5
+    (xa, ya), = list(build(True).take(1))
+    (xb, yb), = list(build(False).take(1))
+    assert _np(xa).shape == (5, 80, 40, 2) and _np(ya).shape == (5, 40, 3)
+    assert np.array_equal(_np(ya), _np(yb))
+    assert nmax_err(_np(xa), _np(xb)) < 1e-4

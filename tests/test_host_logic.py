@@ -82,11 +82,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     from challenge_b200 import _lib
     lib = _lib.load()
     syms = _header_symbols()
-    assert len(syms) >= 14
+    assert len(syms) >= 26
+    assert sorted(_lib.SIGNATURES) == syms, 'include/iris.h and the ctypes binding differ'
     for name in syms:
         assert hasattr(lib, name), 'libiris.so does not export %s' % name
-        assert name in _lib.SIGNATURES or name in _lib._ops_signatures(), \
-            'no ctypes signature for %s' % name
+        assert name in _lib.SIGNATURES, 'no ctypes signature for %s' % name
     assert lib.iris_abi_version() == 1
 
 
@@ -133,3 +133,44 @@ def test_default_mel_matrix_is_the_tf_restatement():
     assert np.array_equal(default_mel_matrix(80), linear_to_mel_weight_matrix(80, 257, 16000))
     assert np.array_equal(default_mel_matrix(40, lower_edge_hertz=80.0, upper_edge_hertz=7600.0),
                           linear_to_mel_weight_matrix(40, 257, 16000, 80.0, 7600.0))
+
+
+def test_dropin_modules_mirror_the_reference_surface():
+    """Every public function of the reference's hot-path modules exists under the same name
+    (SURVEY.md 8b); importing the modules needs neither a GPU nor the oracle."""
+    from challenge_b200 import data_utils, metrics, pipeline, transforms
+    want = {
+        pipeline: ['merge_complex_specs', 'make_pipeline'],
+        transforms: ['mask', 'random_shift', 'magphase_to_mel', 'log_magphase',
+                     'minmax_norm_magphase', 'complex_to_magphase', 'magphase_to_complex',
+                     'phase_vocoder', 'EPSILON'],
+        data_utils: ['load_wav', 'normalize', 'minmax', 'log_on_mel', 'augment', 'to_frame_labels',
+                     'mono_chan', 'stereo_mono', 'label_downsample', 'random_merge_aug',
+                     'multiply_label', 'stft_filter', 'speech_enhancement_preprocess'],
+        metrics: ['er_score', 'f1_score', 'cos_sim'],
+    }
+    for mod, names in want.items():
+        for n in names:
+            assert hasattr(mod, n), '%s.%s missing' % (mod.__name__, n)
+
+
+def test_dataset_lowering_recognises_the_sj_train_chain():
+    """sj_train.make_dataset's stage order (sj_train.py:107-123) lowers to one fused launch."""
+    from challenge_b200 import _lib as L
+    from challenge_b200 import data_utils as D, transforms as TR
+    from challenge_b200.pipeline import IrisDataset
+    ds = IrisDataset({})
+    ds = ds.map(D.to_frame_labels).map(D.augment).map(D.stft_filter(3)).batch(12)
+    ds = ds.map(TR.complex_to_magphase).map(TR.magphase_to_mel(80)).map(D.minmax).map(D.log_on_mel)
+    fused, rest = ds.prefetch(-1)._lower()
+    assert rest == [] and fused['mode'] == L.FEAT_LOGMEL_MINMAX and fused['augment']
+    assert fused['frame_labels'] and fused['filt'] == 3 and fused['n_mels'] == 80
+    # 'nominmax' variant (sj_train.py:121) and a stage the fused kernel does not absorb
+    ds = IrisDataset({}).map(D.to_frame_labels).batch(4).map(TR.complex_to_magphase)
+    ds = ds.map(TR.magphase_to_mel(40)).map(D.log_on_mel).map(D.label_downsample(32))
+    fused, rest = ds._lower()
+    assert fused['mode'] == L.FEAT_LOGMEL and fused['n_mels'] == 40 and len(rest) == 1
+    # out-of-order stages stay un-fused and keep their order
+    ds = IrisDataset({}).map(D.augment).map(D.to_frame_labels).batch(2)
+    fused, rest = ds._lower()
+    assert fused['augment'] and not fused['frame_labels'] and len(rest) == 2
