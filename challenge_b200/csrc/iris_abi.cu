@@ -22,21 +22,31 @@ namespace {
 int set_device(iris_ctx* c) { return iris_set_device(c); }
 
 int build_tables(iris_ctx* c) {
-    // inter-pass twiddles W512^(n2*k1), two k1 per float4: [m][n2] = {k1 = 2m, k1 = 2m + 1}
-    std::vector<float> tw(4 * 256), wh(512);
-    for (int m = 0; m < 16; ++m)
-        for (int n2 = 0; n2 < 16; ++n2)
+    // fftwarp.cuh tables.  tw1[q][n2] = {W512^(n2*2q), W512^(n2*(2q+1))} (inter-pass twiddles);
+    // ts[m][par] = {t(2m), t(2m+1)} with t(i) = par ? W32^i : 1 (radix-2 DIF of pass 2)
+    std::vector<float> tw(8 * 32 * 4), ts(8 * 2 * 4), hann(512);
+    for (int q = 0; q < 8; ++q)
+        for (int n2 = 0; n2 < 32; ++n2)
             for (int h = 0; h < 2; ++h) {
-                const double a = -2.0 * M_PI * double((2 * m + h) * n2) / 512.0;
-                tw[4 * (m * 16 + n2) + 2 * h] = float(cos(a));
-                tw[4 * (m * 16 + n2) + 2 * h + 1] = float(sin(a));
+                const double a = -2.0 * M_PI * double((2 * q + h) * n2) / 512.0;
+                tw[4 * (q * 32 + n2) + 2 * h] = float(cos(a));
+                tw[4 * (q * 32 + n2) + 2 * h + 1] = float(sin(a));
             }
-    // periodic Hann (torch.hann_window(512)), pre-scaled by the 1/2 of the two-channel split
-    for (int n = 0; n < 512; ++n) wh[n] = float(0.5 * (0.5 - 0.5 * cos(2.0 * M_PI * n / 512.0)));
+    for (int m = 0; m < 8; ++m)
+        for (int par = 0; par < 2; ++par)
+            for (int h = 0; h < 2; ++h) {
+                const double a = -2.0 * M_PI * double(2 * m + h) / 32.0;
+                ts[4 * (m * 2 + par) + 2 * h] = par ? float(cos(a)) : 1.f;
+                ts[4 * (m * 2 + par) + 2 * h + 1] = par ? float(sin(a)) : 0.f;
+            }
+    // periodic Hann (torch.hann_window(512)); the 1/2 of the two-channel split rides on the gains
+    for (int n = 0; n < 512; ++n) hann[n] = float(0.5 - 0.5 * cos(2.0 * M_PI * n / 512.0));
     CU(c->tw.reserve(tw.size() * 4));
-    CU(c->whalf.reserve(wh.size() * 4));
+    CU(c->ts.reserve(ts.size() * 4));
+    CU(c->whalf.reserve(hann.size() * 4));
     CU(cudaMemcpy(c->tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->whalf.p, wh.data(), wh.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->ts.p, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->whalf.p, hann.data(), hann.size() * 4, cudaMemcpyHostToDevice));
     CU(c->sched.reserve(16));
     CU(cudaMemset(c->sched.p, 0, 16));
     return IRIS_OK;
@@ -44,26 +54,26 @@ int build_tables(iris_ctx* c) {
 
 void fill_common(iris_ctx* c, FusedParams& p) {
     memset(&p, 0, sizeof(p));
-    p.tw4 = c->tw.as<float4>();
-    p.whalf = c->whalf.as<float>();
+    p.tw1 = c->tw.as<float4>();
+    p.ts = c->ts.as<float4>();
+    p.hann = c->whalf.as<float>();
     p.n_mel = c->n_mel;
     p.mel_f_lo = c->mel_f_lo;
     p.mel_f_n = c->mel_f_n;
     p.mel_taps = c->mel_taps;
-    for (int r = 0; r < 8; ++r) p.mel_L[r] = c->mel_L[r];
+    for (int r = 0; r < 4; ++r) p.mel_L[r] = c->mel_L[r];
     p.mel_info = c->mel_info.as<uint32_t>();
     p.mel_w = c->mel_w.as<float>();
 }
 
-// tile shape of the fused kernel: NP channel pairs x 16/NP frames
-void set_geometry(FusedParams& p, int n_chan) {
+// a tile of the fused kernel is `fr` frames of one (clip, channel pair)
+void set_geometry(iris_ctx* c, FusedParams& p, int n_chan, bool mel) {
     p.C = n_chan;
     p.n_pairs = (n_chan + 1) / 2;
-    int sh = 0;
-    while ((1 << sh) < p.n_pairs && sh < 4) ++sh;
-    p.np_shift = sh;
-    p.n_groups = (p.n_pairs + (1 << sh) - 1) >> sh;
     p.c_out = n_chan;
+    if (!mel) p.mel_taps = 0;   // no mel tables in shared memory
+    p.fr = fused_pick_fr(p.T, p.mel_taps);
+    (void)c;
 }
 
 int ensure_stage(iris_ctx* c, size_t bytes) {
@@ -110,7 +120,7 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
     return IRIS_OK;
 }
 
-// tile-block scratch + scheduler words of a launch, then k_tiles + k_fused
+// tile-block scratch of a launch, then k_tiles + k_fused
 int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
     p.max_segs = max_segs < 1 ? 1 : max_segs;
     int stride = 0;
@@ -119,6 +129,11 @@ int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t 
     p.tile_blocks = c->tiles.as<unsigned char>();
     p.tile_stride = stride;
     p.sched = c->sched.as<uint32_t>();
+    p.chunk = 4;
+    if (const char* e = getenv("IRIS_CHUNK")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4096) p.chunk = v;
+    }
     CU(launch_fused(p, mode, c->num_sms, st));
     return IRIS_OK;
 }
@@ -193,7 +208,7 @@ int iris_ctx_destroy(iris_ctx* c) {
         b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
     }
     for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
-                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->sched,
+                      &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->ts, &c->sched,
                       &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -228,13 +243,15 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     }
     if (f_hi < 0) { f_lo = 0; f_hi = 0; }
     const int f_n = f_hi - f_lo + 1;
-    // groups of 16 filters share a trip count (the longest filter of the group); shorter
-    // filters are zero-padded and shifted so that every tap stays inside [f_lo, f_hi]
-    int L[8] = {0, 0, 0, 0, 0, 0, 0, 0}, taps = 0;
-    for (int m = 0; m < n_mel; ++m) L[m >> 4] = std::max(L[m >> 4], len_of[m]);
-    for (int r = 0; r < 8; ++r) taps += L[r];
-    bool long_filter = false;
-    for (int r = 0; r < 8; ++r) long_filter = long_filter || L[r] > 12;
+    // rounds of 32 filters (filter m = lane + 32 r) share a trip count (the longest filter of
+    // the round); shorter filters are zero-padded and shifted so that every tap stays inside
+    // [f_lo, f_hi]
+    int L[4] = {0, 0, 0, 0}, taps = 0;
+    for (int m = 0; m < n_mel; ++m) L[m >> 5] = std::max(L[m >> 5], len_of[m]);
+    for (int r = 0; r < 4; ++r) {
+        if ((L[r] & 1) && L[r] < f_n) ++L[r];   // even trip counts: the kernel takes two taps per step
+        taps += L[r];
+    }
     // the stand-alone projection (iris_op_mel) takes any matrix: dense weights + column supports
     {
         std::vector<int32_t> lo32(n_mel), len32(n_mel);
@@ -248,19 +265,23 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
         c->mel_bins = n_bins;
         c->n_mel = n_mel;
     }
-    c->mel_fusable = !(f_n > fused_max_mel_window() || taps > fused_max_mel_taps() || long_filter);
+    bool odd = false;
+    for (int r = 0; r < 4; ++r) odd = odd || (L[r] & 1);
+    bool wide = false;
+    for (int r = 0; r < 4; ++r) wide = wide || L[r] > fused_max_mel_filter();
+    c->mel_fusable = taps <= fused_max_mel_taps() && !odd && !wide;
     if (!c->mel_fusable) return IRIS_OK;   // iris_features(mel modes) then reports UNSUPPORTED
     std::vector<uint32_t> info(n_mel, 0);
-    std::vector<float> fw(size_t(std::max(taps, 1)) * 16, 0.f);
+    std::vector<float> fw(size_t(std::max(taps, 1)) * 32, 0.f);
     int row0 = 0;
-    for (int r = 0; r < 8; ++r) {
-        for (int l = 0; l < 16; ++l) {
-            const int m = 16 * r + l;
+    for (int r = 0; r < 4; ++r) {
+        for (int l = 0; l < 32; ++l) {
+            const int m = 32 * r + l;
             if (m >= n_mel || lo_of[m] < 0) continue;
             const int start = std::min(lo_of[m] - f_lo, f_n - L[r]);
             info[m] = uint32_t(start);
             for (int i = 0; i < len_of[m]; ++i)
-                fw[size_t(row0 + (lo_of[m] - f_lo - start) + i) * 16 + l] =
+                fw[size_t(row0 + (lo_of[m] - f_lo - start) + i) * 32 + l] =
                     w[size_t(lo_of[m] + i) * n_mel + m];
         }
         row0 += L[r];
@@ -270,7 +291,7 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     CU(cudaMemcpy(c->mel_info.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->mel_w.p, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
     c->mel_taps = taps;
-    for (int r = 0; r < 8; ++r) c->mel_L[r] = L[r];
+    for (int r = 0; r < 4; ++r) c->mel_L[r] = L[r];
     c->n_mel = n_mel;
     c->mel_f_lo = f_lo;
     c->mel_f_n = f_n;
@@ -362,7 +383,7 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         p.seg_ptr = dp;
         p.B = n_items;
         p.T = b.max_frames;
-        set_geometry(p, n_chan);
+        set_geometry(c, p, n_chan, false);
         p.activity = b.activity.as<uint8_t>();
         rc = run_fused(c, p, FM_ACTIVITY, 1, st);
         if (rc) return rc;
@@ -636,7 +657,7 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     if (mel && c->n_mel == 0) return fail(IRIS_ERR_STATE, "iris_set_mel not called");
     if (mel && !c->mel_fusable)
         return fail(IRIS_ERR_UNSUPPORTED,
-                    "mel matrix spans more than 136 bins or has a filter wider than 12 bins: run "
+                    "a mel filter wider than 16 bins (or more than 64 taps over the 32-filter rounds): run "
                     "IRIS_FEAT_MAGPHASE + iris_op_mel instead of the fused mel epilogue");
     if (mel && c->remap != IRIS_REMAP_NONE)
         return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
@@ -646,7 +667,7 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     p.seg_ptr = c->d_seg_ptr;
     p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
     p.B = c->B; p.T = c->T;
-    set_geometry(p, c->C);
+    set_geometry(c, p, c->C, mel);
     p.c_out = c->c_out;
     p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
     p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
@@ -706,7 +727,7 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
     p.segs = &d->seg;
     p.seg_ptr = d->ptr;
     p.B = 1; p.T = int32_t(kT);
-    set_geometry(p, n_chan);
+    set_geometry(c, p, n_chan, false);
     p.out = d_out;
     return run_fused(c, p, FM_COMPLEX, 1, st);
 }

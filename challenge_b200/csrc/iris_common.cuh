@@ -39,9 +39,8 @@ struct FusedParams {
     const int32_t* seg_ptr;  // [B+1]
     const uint8_t* keep;     // voice accept flags, may be null
     int32_t B, T, C;         // clips, frames per clip, input channels
-    int32_t n_pairs;         // ceil(C/2)
-    int32_t np_shift;        // log2(NP): a tile is (16 >> np_shift) frames x NP channel pairs
-    int32_t n_groups;        // ceil(n_pairs / NP)
+    int32_t n_pairs;         // ceil(C/2): a tile is `fr` frames of one (clip, channel pair)
+    int32_t fr;              // frames per tile = consumer warps per CTA
     int32_t c_out;           // output channels (C unless remapped)
     // SpecAugment rectangles (size, offset) per clip; null => none
     const int32_t* tmask;
@@ -52,30 +51,32 @@ struct FusedParams {
     int32_t remap;
     const float* merge_f;   // [B, c_out-2] factor
     const float* merge_sf;  // [B, c_out-2] sqrt(1-factor)
-    // per-tile stage lists (k_tiles -> k_fused) and the dynamic tile scheduler
+    // per-tile stage lists (k_tiles -> k_fused)
     unsigned char* tile_blocks;  // [n_tiles] blocks of tile_stride bytes
     int32_t tile_stride;
     int32_t max_segs;            // most mixing segments any clip has
-    uint32_t* sched;             // [2] next tile, CTAs finished; zero between launches
+    int32_t chunk;               // consecutive tiles per work claim
+    uint32_t* sched;             // [2] next chunk, CTAs finished; zero between launches
     // outputs
     float* out;             // layout depends on mode
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
     int32_t do_log, do_minmax;
     uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); k_logmel_post re-zeroes it
-    // mel projection: filters are handled in groups of 16 (m = lane + 16 r); every filter of
-    // group r reads mel_L[r] consecutive magnitudes starting at bin mel_f_lo + mel_info[m]
-    // (shorter filters are zero-padded), weights at mel_w[(row0(r) + i) * 16 + lane]
+    // mel projection: filters are handled in rounds of 32 (m = lane + 32 r); every filter of
+    // round r reads mel_L[r] consecutive magnitudes starting at bin mel_f_lo + mel_info[m]
+    // (shorter filters are zero-padded), weights at mel_w[(row0(r) + i) * 32 + lane]
     int32_t n_mel;
     int32_t mel_f_lo;       // lowest bin with a non-zero weight
     int32_t mel_f_n;        // number of bins in [f_lo, f_hi]
     int32_t mel_taps;       // sum of mel_L
-    int32_t mel_L[8];
+    int32_t mel_L[4];
     const uint32_t* mel_info;  // [n_mel] first tap, relative to mel_f_lo
-    const float* mel_w;        // [mel_taps][16]
-    // tables
-    const float4* tw4;      // [16][16] {W512^(n2*2m), W512^(n2*(2m+1))}
-    const float* whalf;     // [512] 0.5 * hann
+    const float* mel_w;        // [mel_taps][32]
+    // tables (fftwarp.cuh)
+    const float4* tw1;      // [8][32] {W512^(n2*2q), W512^(n2*(2q+1))}
+    const float4* ts;       // [8][2]  {t(2m), t(2m+1)}, t(i) = par ? W32^i : 1
+    const float* hann;      // [512] periodic Hann
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----
@@ -110,6 +111,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+// wait with exponential back-off: a warp that polls in a tight loop takes issue slots from
+// the warps that have work; the first polls stay quick because data is usually about to land
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns0,
+                                                  unsigned ns_max) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned ns = ns0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        ns = min(2u * ns, ns_max);
+    }
+}
+// arrive from the lanes where `pred` holds, as ONE predicated instruction (an `if` around
+// mbar_arrive splits the warp until the next reconvergence point)
+__device__ __forceinline__ void mbar_arrive_if(uint64_t* bar, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(uint32_t(pred))
+        : "memory");
+}
+// fire-and-forget atomic max (no return value: nothing to wait for)
+__device__ __forceinline__ void red_max_u32_if(uint32_t* addr, uint32_t v, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p red.global.max.u32 [%0], %1;\n\t}" ::"l"(addr),
+        "r"(v), "r"(uint32_t(pred))
+        : "memory");
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

@@ -73,10 +73,10 @@ struct iris_ctx {
     int device = 0;
     int num_sms = 148;
     Bank banks[3];
-    DevBuf tw, whalf;
+    DevBuf tw, ts, whalf;
     // mel (CSR by mel bin)
     int n_mel = 0, mel_f_lo = 0, mel_f_n = 0, mel_taps = 0;
-    int mel_L[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int mel_L[4] = {0, 0, 0, 0};
     DevBuf mel_info, mel_w;
     // plan
     bool has_plan = false, labels_done = false;

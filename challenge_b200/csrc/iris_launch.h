@@ -10,8 +10,10 @@ struct FusedParams;
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
 int fused_max_segments();      // mixing segments one clip may have
-int fused_max_mel_window();    // widest bin range [f_lo, f_hi] of the mel matrix
-int fused_max_mel_taps();      // sum over 16-filter groups of the longest filter
+int fused_max_mel_taps();      // sum over the 32-filter rounds of the longest filter
+int fused_max_mel_filter();    // taps of the longest filter
+int fused_max_frames_per_tile();
+int fused_pick_fr(int T, int mel_taps);   // frames per tile (consumer warps per CTA)
 size_t fused_tile_bytes(const FusedParams& p, int* stride_out);   // size of p.tile_blocks
 
 // k_post.cu

@@ -1,8 +1,8 @@
-// Fused hot path (v4): gather + time-domain mix of the gained source frames (TMA bulk
-// copies into a 2-slot shared-memory ring), window, 512-point FFT per frame (two real
-// channels packed into one complex transform, one half-warp per FFT), then the epilogue
-// (SpecAugment masks, channel remap, stft_filter, complex / mag-phase / log-mag-phase
-// output, or magnitude -> sparse mel -> per-clip min-max -> log), writing each feature once.
+// Fused hot path (v5): gather + time-domain mix of the gained source frames, window,
+// 512-point FFT per frame (two real channels packed into one complex transform, ONE WARP per
+// frame, 16 points per lane), then the epilogue (SpecAugment masks, channel remap,
+// stft_filter, complex / mag-phase / log-mag-phase output, or magnitude -> sparse mel ->
+// per-clip min-max), writing each feature once.
 //
 // Replaces, for one output clip, the chain
 //   data_utils.load_wav (STFT, data_utils.py:9-29)  ->  pipeline.merge_complex_specs
@@ -12,97 +12,93 @@
 //   ->  data_utils.log_on_mel (50-55)
 // using linearity of the STFT: sum_k g_k STFT(src_k)[frame] = FFT(w * sum_k g_k frame_k).
 //
-// Structure.  A tile is FR = 16/NP output frames x NP channel pairs of one clip (NP = 1 for
-// <= 2 channels, 2 for <= 4, ...): 16 half-warp FFT slots, 8 warps, 2 CTAs per SM.
+// Structure.  A tile is FR consecutive output frames of one (clip, channel pair); a CTA has
+// FR consumer warps (warp j owns frame j of the tile) and one producer warp.
 //  * k_tiles (one thread per tile) compacts, for every tile, the mixing segments that are
 //    kept and overlap it into a TileBlock (stage descriptors + the tile's mask bits).
-//  * k_fused CTAs claim tiles from a global counter (dynamic scheduling) and stream the
-//    TileBlocks of the next tiles into an 8-deep shared-memory ring with cp.async, three
-//    tiles ahead; every ring entry has an mbarrier that completes when its block has landed.
-//  * Every stage of a tile is (FR+1) 2 KB rows per pair, fetched with one cp.async.bulk per
-//    pair into slot (stage & 1) and consumed by all 8 warps.  There is no producer warp: the
-//    LAST warp to finish reading a slot (shared-memory counter) issues the copy of stage+2
-//    into it, so loads run two stages ahead while the FFTs execute.
-//  * There is NO CTA-wide barrier in the tile loop: warps are coupled only through the slot
-//    protocol (a warp runs at most two stages ahead of the slowest one), so mix, FFT and
-//    epilogue phases of different warps overlap.  Every warp stores its own frames.
+//  * Tiles are claimed in chunks of consecutive tiles from a global counter.  The producer warp
+//    copies the TileBlock of each tile into a shared-memory descriptor ring and fetches every
+//    stage -- (j_cnt + 1) contiguous 2 KB rows of the pair-interleaved bank -- with ONE
+//    cp.async.bulk (TMA 1-D) into a ring of kSlots stage buffers: full[slot] completes when
+//    the bytes have landed, empty[slot] when all FR consumer warps have read the slot.
+//  * Consumer warps never synchronise with each other: each waits on full[slot], accumulates
+//    gain * frame into its 16 complex registers per lane, releases the slot, and after the
+//    last stage runs the warp FFT (fftwarp.cuh: 16-point FFT in registers, twiddle, one
+//    exchange through its private 4.25 KB of shared memory, radix-2 DIF + 16-point FFT) and
+//    the epilogue.  Rows shared by adjacent frames are read from the same slot, so every
+//    source row enters the SM once per tile.
 //  * LOGMEL_MINMAX: per-warp min/max go to global atomics; k_logmel_post (k_post.cu)
-//    normalises and logs the batch in place right after, while it is still in L2.  (An
-//    in-kernel tail run by the CTA that completes a clip was measured 35 % slower: the CTA
-//    that falls behind becomes the last finisher of every clip it touches.)
+//    normalises and logs the batch in place right after, while it is still in L2.
+#include "fftwarp.cuh"
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
 namespace iris {
 
-constexpr int kSlots = 16;       // half-warp FFT slots per CTA
-constexpr int kWarps = 8;
-constexpr int kThreads = 256;
-constexpr int kRing = 8;         // TileBlock ring entries per CTA (>= 6: see the skew bound below)
+constexpr int kSlots = 3;        // stage buffers per CTA
+constexpr int kRing = 8;         // TileBlock ring entries (> kSlots + 1, see the producer)
 constexpr int kMaxStages = 16;   // mixing segments of one clip (upper bound on stages per tile)
+#ifndef IRIS_MAX_FR
+#define IRIS_MAX_FR 16
+#endif
+#ifndef IRIS_MAX_REGS
+#define IRIS_MAX_REGS 96   // no spills; 2 CTAs x 9 warps (FR = 8) or 17 warps (FR = 16) per SM fit the register file
+#endif
+constexpr int kMaxFR = IRIS_MAX_FR;   // consumer warps per CTA (sets the register budget)
 constexpr int kMaxMel = 128;
-constexpr int kMaxTaps = 64;     // sum over the 16-filter groups of the longest filter in the group
+constexpr int kMaxTaps = 64;     // sum over the 32-filter rounds of the longest filter
+constexpr int kMaxFilter = 16;   // taps of the longest mel filter the fused epilogue takes
 
 struct StageDesc {
-    const float* src;      // first row of pair plane (group * NP) of the source
-    uint32_t pair_stride;  // floats between pair planes
-    uint16_t j_lo, j_cnt;  // tile-relative frames [j_lo, j_lo + j_cnt); j_cnt == 0: empty tile
-    float gain;
-    uint32_t pad_;
+    const float* src;      // first row of the stage in the pair plane of the source
+    uint16_t j_lo, j_cnt;  // tile-relative frames [j_lo, j_lo + j_cnt); j_cnt == 0: empty stage
+    float gain;            // 0.5 * gain (the 1/2 of the two-channel split)
 };
-static_assert(sizeof(StageDesc) == 24, "StageDesc layout");
+static_assert(sizeof(StageDesc) == 16, "StageDesc layout");
 
 struct TileBlock {
-    int32_t n;             // stages (>= 1); 0 = end of work
+    int32_t n;             // stages (>= 1)
     int32_t b;             // clip
-    int32_t t0_group;      // first frame | group << 24
+    int32_t t0_pair;       // first frame | pair << 24
     uint32_t tmask_bits;   // bit j: frame t0 + j is time-masked (transforms.py:12-40)
     int16_t fm[8];         // (size, offset) x 4 frequency masks of the clip
     StageDesc d[kMaxStages];
 };
-static_assert(sizeof(TileBlock) == 32 + 24 * kMaxStages, "TileBlock layout");
+static_assert(sizeof(TileBlock) == 32 + 16 * kMaxStages, "TileBlock layout");
 constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
 // ---- shared memory map (bytes) ----
-constexpr int OFF_FULL = 0;      // uint64 full[2]      slot s holds a complete stage
-constexpr int OFF_CNT = 16;      // int cnt[2]          warps done reading slot s
-constexpr int OFF_CLAIM = 32;    // int claimed[3]      first tiles of the CTA
-constexpr int OFF_RFULL = 64;    // uint64 rfull[8]     ring entry k & 7 has landed
-constexpr int OFF_RING = 128;
-constexpr int OFF_TW = OFF_RING + kRing * kTileBlockBytes;
-constexpr int OFF_WH = OFF_TW + 256 * 16;
-constexpr int OFF_MINFO = OFF_WH + 512 * 4;
-constexpr int OFF_MW = OFF_MINFO + kMaxMel * 4;
-constexpr int OFF_XCH = OFF_MW + kMaxTaps * 16 * 4;
-constexpr int OFF_SLOTS = OFF_XCH + kSlots * kXchSlotFloats * 4;
-static_assert(OFF_SLOTS % 128 == 0, "slot alignment");
+constexpr int OFF_FULL = 0;                                  // uint64 full[kSlots]
+constexpr int OFF_EMPTY = 32;                                // uint64 empty[kSlots]
+constexpr int OFF_RING = 64;
+constexpr int OFF_TW1 = OFF_RING + kRing * kTileBlockBytes;  // float4 [8][32]
+constexpr int OFF_TS = OFF_TW1 + 8 * 32 * 16;                // float4 [8][2]
+constexpr int OFF_MSTART = OFF_TS + 8 * 2 * 16;              // uint32 [kMaxMel]
+constexpr int OFF_MW = OFF_MSTART + kMaxMel * 4;             // float [mel_taps][32]
+static_assert(OFF_TW1 % 16 == 0 && OFF_MW % 16 == 0, "table alignment");
 
-__host__ __device__ inline uint32_t slot_bytes(int np_shift) {
-    return (1u << np_shift) * ((16u >> np_shift) + 1u) * 2048u;
+__host__ __device__ inline uint32_t off_xch(int mel_taps) {
+    return (uint32_t(OFF_MW) + uint32_t(mel_taps) * 128u + 127u) & ~127u;
 }
-__host__ __device__ inline uint32_t smem_total(int np_shift) {
-    return OFF_SLOTS + 2 * slot_bytes(np_shift);
+__host__ __device__ inline uint32_t off_slots(int mel_taps, int fr) {
+    return off_xch(mel_taps) + uint32_t(fr) * uint32_t(kXwBytes);   // kXwBytes % 128 == 0
 }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-// arrive on an mbarrier once all cp.async of this thread issued so far have landed
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__host__ __device__ inline uint32_t slot_bytes(int fr) { return uint32_t(fr + 1) * 2048u; }
+__host__ __device__ inline uint32_t smem_total(int mel_taps, int fr) {
+    return off_slots(mel_taps, fr) + kSlots * slot_bytes(fr);
 }
 
 // ---- pre-kernel: one thread per tile builds its TileBlock ----
 __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
-    const int FR = 16 >> p.np_shift;
+    const int FR = p.fr;
     const int tpc = (p.T + FR - 1) / FR;
-    const int per_clip = tpc * p.n_groups;
+    const int per_clip = tpc * p.n_pairs;
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= p.B * per_clip) return;
     const int b = tile / per_clip;
     const int r = tile - b * per_clip;
-    const int group = r / tpc;
-    const int t0 = (r - group * tpc) * FR;
+    const int pair = r / tpc;
+    const int t0 = (r - pair * tpc) * FR;
     const int t_end = min(t0 + FR, p.T);
     unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
     StageDesc* d = reinterpret_cast<StageDesc*>(blk + 32);
@@ -114,19 +110,16 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
         if (lo >= hi || (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0)) continue;
         if (n < p.max_segs) {
             StageDesc e;
-            e.src = sg.base + size_t(group << p.np_shift) * size_t(sg.pair_stride) +
-                    size_t(lo + sg.shift) * 512;
-            e.pair_stride = uint32_t(sg.pair_stride);
+            e.src = sg.base + size_t(pair) * size_t(sg.pair_stride) + size_t(lo + sg.shift) * 512;
             e.j_lo = uint16_t(lo - t0);
             e.j_cnt = uint16_t(hi - lo);
-            e.gain = sg.gain;
-            e.pad_ = 0;
+            e.gain = 0.5f * sg.gain;   // exact; folds the 1/2 of the two-channel split
             d[n++] = e;
         }
     }
-    if (n == 0) {   // nothing overlaps: one empty stage keeps the ring protocol uniform
+    if (n == 0) {   // nothing overlaps: one empty stage keeps the slot protocol uniform
         StageDesc e;
-        e.src = nullptr; e.pair_stride = 0; e.j_lo = 0; e.j_cnt = 0; e.gain = 0.f; e.pad_ = 0;
+        e.src = nullptr; e.j_lo = 0; e.j_cnt = 0; e.gain = 0.f;
         d[n++] = e;
     }
     uint32_t tbits = 0;
@@ -139,7 +132,7 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
         }
     }
     int4 hdr;
-    hdr.x = n; hdr.y = b; hdr.z = t0 | (group << 24); hdr.w = int(tbits);
+    hdr.x = n; hdr.y = b; hdr.z = t0 | (pair << 24); hdr.w = int(tbits);
     *reinterpret_cast<int4*>(blk) = hdr;
     int16_t fm[8];
 #pragma unroll
@@ -152,25 +145,6 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
         }
     }
     *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
-}
-
-__device__ __forceinline__ void issue_stage(const StageDesc* dp, uint32_t slot_addr, uint32_t full_addr,
-                                            int np_here, uint32_t plane_bytes) {
-    const StageDesc d = *dp;
-    if (d.j_cnt == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_addr) : "memory");
-        return;
-    }
-    const uint32_t bytes = (uint32_t(d.j_cnt) + 1u) * 2048u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_addr),
-                 "r"(bytes * uint32_t(np_here))
-                 : "memory");
-    for (int pr = 0; pr < np_here; ++pr)
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                "r"(slot_addr + pr * plane_bytes + uint32_t(d.j_lo) * 2048u),
-            "l"(d.src + size_t(pr) * d.pair_stride), "r"(bytes), "r"(full_addr)
-            : "memory");
 }
 
 template <int MODE>
@@ -236,490 +210,432 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
     }
 }
 
-// KB: number of 32-bin groups the epilogue needs (mel support below bin 32*KB); 8 = all bins.
-template <int MODE, int KB>
-__global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ FusedParams p) {
+// NJ: output registers per lane the epilogue needs: 4 = bins below 128 only (mel matrices
+// whose support ends below bin 128), 8 = all 257 bins.
+template <int MODE, int NJ>
+__global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr bool kMel = (MODE == FM_MEL);
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, n2 = lane & 15;
-    const uint32_t sm_base = smem_u32(sm);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int FR = p.fr;
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
-    uint64_t* rfull = reinterpret_cast<uint64_t*>(sm + OFF_RFULL);
-    int* cnt = reinterpret_cast<int*>(sm + OFF_CNT);
-    int* claimed = reinterpret_cast<int*>(sm + OFF_CLAIM);
-    float4* s_tw4 = reinterpret_cast<float4*>(sm + OFF_TW);
-    float* s_wh = reinterpret_cast<float*>(sm + OFF_WH);
-    uint32_t* s_minfo = reinterpret_cast<uint32_t*>(sm + OFF_MINFO);
-    float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
-    auto ring = [&](int k) -> TileBlock* {
-        return reinterpret_cast<TileBlock*>(sm + OFF_RING + (k & (kRing - 1)) * kTileBlockBytes);
-    };
-    const int NP = 1 << p.np_shift;
-    const int FR = 16 >> p.np_shift;
-    const int n_tiles = p.B * ((p.T + FR - 1) / FR) * p.n_groups;
-    const uint32_t slotB = slot_bytes(p.np_shift);
-    const uint32_t planeB = uint32_t(FR + 1) * 2048u;
+    uint64_t* empty = reinterpret_cast<uint64_t*>(sm + OFF_EMPTY);
+    const int n_tiles = p.B * ((p.T + FR - 1) / FR) * p.n_pairs;
+    const uint32_t slotB = slot_bytes(FR);
+    unsigned char* slots = sm + off_slots(p.mel_taps, FR);
 
-    // one warp streams the TileBlock of `tile` into ring entry k (or writes the end marker);
-    // completion is signalled later by fetch_done(k) (32 arrivals on rfull[k & 7])
-    auto fetch_block = [&](int k, int tile) {
-        TileBlock* dst = ring(k);
-        if (tile < n_tiles) {
-            const unsigned char* src = p.tile_blocks + size_t(tile) * p.tile_stride;
-            const uint32_t d0 = smem_u32(dst);
-            for (int c = lane * 16; c < p.tile_stride; c += 32 * 16) cp_async16(d0 + c, src + c);
-        } else {
-            if (lane == 0) dst->n = 0;
-            __threadfence_block();
-        }
-    };
-    auto fetch_done = [&](int k) { cp_async_arrive(&rfull[k & (kRing - 1)]); };
-
-    for (int i = tid; i < 256; i += kThreads) s_tw4[i] = p.tw4[i];
-    for (int i = tid; i < 512; i += kThreads) s_wh[i] = p.whalf[i];
-    if (kMel) {
-        for (int i = tid; i < kMaxMel; i += kThreads) s_minfo[i] = i < p.n_mel ? p.mel_info[i] : 0u;
-        for (int i = tid; i < p.mel_taps * 16; i += kThreads) s_mw[i] = p.mel_w[i];
-    }
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        for (int i = 0; i < kRing; ++i) mbar_init(&rfull[i], 32);
-        cnt[0] = 0;
-        cnt[1] = 0;
-        fence_mbar_init();
-        // the first three tiles of this CTA, in order (an end marker must never precede work)
-        const int c = int(atomicAdd(&p.sched[0], 3u));
-        for (int i = 0; i < 3; ++i) claimed[i] = c + i;
-    }
-    __syncthreads();
-    if (warp < 3) {
-        fetch_block(warp, claimed[warp]);
-        fetch_done(warp);
-    }
-
-    // ring entries 0 .. ready are known to have landed (per warp; entries land in order)
-    int ready = -1;
-    auto ensure = [&](int k) {
-        while (ready < k) {
-            ++ready;
-            mbar_wait(&rfull[ready & (kRing - 1)], uint32_t(ready >> 3) & 1u);
-        }
-    };
-    // issue cursor = position (tile iteration ki, entry ei) of stage q + 2
-    int ki = 0, ei = 0;
-    auto advance = [&]() {
-        ensure(ki);
-        const int n = ring(ki)->n;
-        if (n != 0 && ++ei >= n) { ++ki; ei = 0; }
-    };
-    auto np_of = [&](int k) { return min(NP, p.n_pairs - ((ring(k)->t0_group >> 24) << p.np_shift)); };
-    ensure(1);
-    if (tid == 0) {
-        int a = 0, e = 0;
-        for (int s = 0; s < 2; ++s) {
-            const TileBlock* tb = ring(a);
-            if (tb->n == 0) break;
-            issue_stage(&tb->d[e], sm_base + OFF_SLOTS + s * slotB, sm_base + OFF_FULL + 8 * s, np_of(a), planeB);
-            if (++e >= tb->n) { ++a; e = 0; }
-        }
-    }
-    advance();
-    advance();
-
-    const int slot = warp * 2 + (lane >> 4);
-    const unsigned hmask = (lane >> 4) ? 0xFFFF0000u : 0x0000FFFFu;
-    float* xs = reinterpret_cast<float*>(sm + OFF_XCH) + slot * kXchSlotFloats;
-    const int ka = n2, kb = (n2 == 0) ? 16 : 32 - n2;
-    const bool l0 = (n2 == 0);
-    const int j = slot >> p.np_shift;          // tile-relative frame of this slot
-    const int pr = slot & (NP - 1);            // pair within the tile's group
-    const float2* my_rows = reinterpret_cast<const float2*>(sm + OFF_SLOTS + pr * planeB) + j * 256 + n2;
-    // running per-clip extrema of this lane (flushed when the clip changes)
-    float mn = __int_as_float(0x7f800000), mx = 0.f;
-    int mm_clip = -1;
-    auto flush_minmax = [&]() {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
-        if (lane == 0 && mn <= mx) {
-            atomicMax(&p.minmax[2 * mm_clip], ~__float_as_uint(mn));
-            atomicMax(&p.minmax[2 * mm_clip + 1], __float_as_uint(mx));
-        }
-        mn = __int_as_float(0x7f800000);
-        mx = 0.f;
-    };
-
-    int q = 0;          // stages consumed so far
-    for (int k = 0;; ++k) {
-        ensure(k);
-        const TileBlock* tb = ring(k);
-        const int n_st = tb->n;
-        if (n_st == 0) break;
-        // Skew bound: a slot is refilled only after all 8 warps have read it and every tile
-        // has at least one stage, so no warp is more than two tiles ahead of the slowest one;
-        // entry k+3 therefore never overwrites an entry (>= k-2) that is still being read.
-        int new_claim = 0;
-        // one fixed builder warp: its claims are then ordered like the ring entries (an end
-        // marker must never precede a valid tile)
-        const bool builder = warp == 0;
-        // the builder warp of this iteration claims the tile of ring entry k+3 now and streams
-        // its block at the end of the iteration, when the atomic has long returned
-        if (builder && lane == 0) new_claim = int(atomicAdd(&p.sched[0], 1u));
-
-        // ---- gather + mix: acc = sum over the stages of this tile of gain * frame ----
-        float re[32], im[32];
-        const int group = tb->t0_group >> 24;
-        const bool pair_ok = (group << p.np_shift) + pr < p.n_pairs;
-        // wait for stage e of this tile; returns the gain, or sets active = false
-        auto stage_begin = [&](int e, bool& active) -> float {
-            const uint32_t jj = *reinterpret_cast<const uint32_t*>(&tb->d[e].j_lo);   // j_lo | j_cnt << 16
-            const float gn = tb->d[e].gain;
-            mbar_wait(&full[q & 1], uint32_t(q >> 1) & 1u);
-            active = pair_ok && unsigned(j - int(jj & 0xffffu)) < (jj >> 16);
-            return gn;
-        };
-        // this warp is done reading the slot; the last warp to say so refills it
-        auto stage_end = [&]() {
-            const int s = q & 1;
-            __syncwarp();
-            if (lane == 0) {
-                const int old = atomicAdd(&cnt[s], 1);
-                if (old == kWarps - 1) {
-                    cnt[s] = 0;
-                    if (ready < ki) mbar_wait(&rfull[ki & (kRing - 1)], uint32_t(ki >> 3) & 1u);
-                    const TileBlock* nb = ring(ki);
-                    if (nb->n != 0) {
-                        fence_proxy_async();
-                        issue_stage(&nb->d[ei], sm_base + OFF_SLOTS + s * slotB, sm_base + OFF_FULL + 8 * s,
-                                    np_of(ki), planeB);
-                    }
-                }
-            }
-            ++q;
-            advance();
-        };
-        {   // first stage initialises the accumulators
-            bool active;
-            const float gn = stage_begin(0, active);
-            const float2* src = reinterpret_cast<const float2*>(
-                reinterpret_cast<const unsigned char*>(my_rows) + (q & 1) * slotB);
-            const float g0 = active ? gn : 0.f;
-            if (!active) src = reinterpret_cast<const float2*>(sm + OFF_TW);   // 4 KB of finite data
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float2 x = src[16 * i];
-                re[i] = g0 * x.x;
-                im[i] = g0 * x.y;
-            }
-            stage_end();
-        }
-        for (int e = 1; e < n_st; ++e) {
-            bool active;
-            const float gn = stage_begin(e, active);
-            if (active) {
-                const float2* src = reinterpret_cast<const float2*>(
-                    reinterpret_cast<const unsigned char*>(my_rows) + (q & 1) * slotB);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float2 x = src[16 * i];
-                    re[i] = fmaf(gn, x.x, re[i]);
-                    im[i] = fmaf(gn, x.y, im[i]);
-                }
-            }
-            stage_end();
-        }
-
-        const int b = tb->b;
-        const int t0 = tb->t0_group & 0xffffff;
-        const int t = t0 + j;
-        const int pair = (group << p.np_shift) + pr;
-        const bool in_range = t < p.T && pair_ok;
-        const bool has1 = (2 * pair + 1 < p.C);
-        // SpecAugment time mask of this frame (transforms.py:12-40), precomputed per tile
-        const float mt = ((tb->tmask_bits >> j) & 1u) ? 0.f : 1.f;
-        // a fully time-masked frame has zero magnitude everywhere: no FFT needed for mel
-        const bool do_fft = in_range && !(kMel && mt == 0.f);
-
-        cpx Za[16], Zb[16];
-        if (do_fft) {
-            cpx v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float w = s_wh[16 * i + n2];
-                v[i] = cpx{re[i] * w, im[i] * w};
-            }
-            Fft<32>::run(v);
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const float4 w = s_tw4[m * 16 + n2];
-                if (m > 0) v[2 * m] = cmul(v[2 * m], cpx{w.x, w.y});
-                v[2 * m + 1] = cmul(v[2 * m + 1], cpx{w.z, w.w});
-            }
-            // ---- exchange through shared memory, 4 rounds of 8 k1: Za (k1 = ka < 16) is
-            // served by rounds 0-1, Zb (k1 = kb >= 16) by rounds 2-3 ----
-#pragma unroll
-            for (int rho = 0; rho < 4; ++rho) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    *reinterpret_cast<float4*>(xs + xch_write_off(a, n2)) =
-                        make_float4(v[8 * rho + 2 * a].x, v[8 * rho + 2 * a].y,
-                                    v[8 * rho + 2 * a + 1].x, v[8 * rho + 2 * a + 1].y);
-                __syncwarp(hmask);
-                if (rho < 2) {
-                    if ((ka >> 3) == rho) {
-#pragma unroll
-                        for (int jx = 0; jx < 16; ++jx) {
-                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(ka & 7, jx));
-                            Za[jx] = cpx{z.x, z.y};
-                        }
-                    }
-                } else {
-                    if ((kb >> 3) == rho) {
-#pragma unroll
-                        for (int jx = 0; jx < 16; ++jx) {
-                            const float2 z = *reinterpret_cast<const float2*>(xs + xch_read_off(kb & 7, jx));
-                            Zb[jx] = cpx{z.x, z.y};
-                        }
-                    }
-                }
-                __syncwarp(hmask);
-                // Za is complete after round 1: transform it now, while only v[16..31] is
-                // still live, instead of holding v, Za and Zb together
-                if (rho == 1) Fft<16>::run(Za);
-            }
-            Fft<16>::run(Zb);
-        }
-
-        // ---- epilogue ----
-        // bin f = ka+32*k2 pairs with its mirror 512-f held in Zb[15-k2] (lane 0: Za[(16-k2)&15]);
-        // bin f = kb+32*k2 pairs with Za[15-k2] (lane 0: Zb[15-k2]).  The 0.5 of the
-        // two-channel split is folded into the window table.
+    // ---- one-time setup: tables, barriers, finite data in the stage buffers ----
+    {
+        float4* s_tw1 = reinterpret_cast<float4*>(sm + OFF_TW1);
+        for (int i = tid; i < 8 * 32; i += blockDim.x) s_tw1[i] = p.tw1[i];
+        float4* s_ts = reinterpret_cast<float4*>(sm + OFF_TS);
+        for (int i = tid; i < 16; i += blockDim.x) s_ts[i] = p.ts[i];
         if (kMel) {
-            if (p.do_minmax && b != mm_clip) {
-                if (mm_clip >= 0) flush_minmax();
-                mm_clip = b;
+            uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
+            for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = i < p.n_mel ? p.mel_info[i] : 0u;
+            float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
+            for (int i = tid; i < p.mel_taps * 32; i += blockDim.x) s_mw[i] = p.mel_w[i];
+        }
+        // rows of a slot outside a stage's frame range are read (and multiplied by 0) by the
+        // frames the stage does not cover: they must hold finite numbers
+        float4* z = reinterpret_cast<float4*>(slots);
+        for (uint32_t i = tid; i < kSlots * slotB / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid == 0) {
+            for (int s = 0; s < kSlots; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], uint32_t(FR));
             }
-            float2* mg = reinterpret_cast<float2*>(xs);   // [mel_f_n] (|ch0|, |ch1|), aliases the exchange slot
-            const int f_lo = p.mel_f_lo, f_n = p.mel_f_n;
-            float acc0[8], acc1[8];   // mel bins m = n2 + 16 r
+            fence_mbar_init();
+        }
+        fence_proxy_async();   // the zero fill (generic proxy) precedes the bulk copies (async proxy)
+        __syncthreads();
+    }
+
+    if (warp == FR) {
+        // =========================== producer warp ===========================
+        // The producer is at most kSlots stages ahead of the slowest consumer and every tile
+        // has at least one stage, so when it writes ring entry i the slowest consumer is
+        // still in tile >= i - kSlots - 1: kRing > kSlots + 1 entries never collide.
+        // Work is claimed in chunks of p.chunk consecutive tiles from a global counter (the
+        // next claim is issued one chunk ahead, so its latency is hidden): consecutive tiles of
+        // a clip mostly stay on one SM (per-clip state changes rarely, the row shared by two
+        // tiles is re-read one tile later) and the SMs still finish together.
+        uint32_t slot = 0, phase = 0;
+        const int chunks16 = p.tile_stride >> 4;
+        const int CH = p.chunk;
+        int i = 0;
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(&p.sched[0], 1u);
+        while (true) {
+            const long long first = (long long)__shfl_sync(0xffffffffu, next, 0) * CH;
+            if (first >= n_tiles) break;
+            if (lane == 0) next = atomicAdd(&p.sched[0], 1u);
+            const int last = int(min((long long)n_tiles, first + CH));
+            for (int tile = int(first); tile < last; ++tile, ++i) {
+                const unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
+                unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
+                int4 c = make_int4(0, 0, 0, 0);
+                if (lane < chunks16) {
+                    c = __ldg(reinterpret_cast<const int4*>(blk) + lane);
+                    *reinterpret_cast<int4*>(ent + 16 * lane) = c;
+                }
+                __syncwarp();
+                const int n = __shfl_sync(0xffffffffu, c.x, 0);
+                const TileBlock* tb = reinterpret_cast<const TileBlock*>(ent);
+                for (int s = 0; s < n; ++s) {
+                    // the whole warp waits (one instruction per poll either way) so that it stays
+                    // converged; polls back off because a slot frees up once per ~microsecond
+                    mbar_wait_backoff(&empty[slot], phase ^ 1u, 128, 512);
+                    if (lane == 0) {
+                        const StageDesc d = tb->d[s];
+                        if (d.j_cnt == 0) {
+                            mbar_arrive(&full[slot]);
+                        } else {
+                            const uint32_t bytes = (uint32_t(d.j_cnt) + 1u) * 2048u;
+                            mbar_arrive_expect_tx(&full[slot], bytes);
+                            bulk_g2s(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot]);
+                        }
+                    }
+                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                }
+            }
+        }
+        // end marker: a TileBlock with n == 0 behind one more (empty) stage
+        {
+            unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
+            if (lane == 0) *reinterpret_cast<int4*>(ent) = make_int4(0, 0, 0, 0);
+            __syncwarp();
+            mbar_wait_backoff(&empty[slot], phase ^ 1u, 128, 512);
+            if (lane == 0) {
+                mbar_arrive(&full[slot]);
+                // the last CTA to get here resets the work counter for the next launch
+                if (atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+                    p.sched[0] = 0u;
+                    p.sched[1] = 0u;
+                }
+            }
+        }
+    } else {
+        // =========================== consumer warps ===========================
+        const int j = warp;                        // tile-relative frame of this warp
+        const int k1 = warp_k1(lane), par = warp_par(lane);
+        const float sgn = par ? -1.f : 1.f;
+        const int partner = warp_partner(lane);
+        const bool l0 = (lane == 0);
+        float w8[8];                               // Hann[n], n = lane + 32 i; Hann[n + 256] = 1 - Hann[n]
 #pragma unroll
-            for (int r = 0; r < 8; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+        for (int i = 0; i < 8; ++i) w8[i] = p.hann[lane + 32 * i];
+        unsigned char* xch = sm + off_xch(p.mel_taps) + warp * kXwBytes;
+        const float4* s_tw1 = reinterpret_cast<const float4*>(sm + OFF_TW1) + lane;
+        const float4* s_ts = reinterpret_cast<const float4*>(sm + OFF_TS) + par;
+        const unsigned char* my_rows = slots + j * 2048 + lane * 8;
+        // running per-clip extrema of this lane (flushed when the clip changes)
+        float mn = __int_as_float(0x7f800000), mx = 0.f;
+        int mm_clip = -1;
+        auto flush_minmax = [&]() {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            const bool go = lane == 0 && mn <= mx;
+            red_max_u32_if(&p.minmax[2 * mm_clip], ~__float_as_uint(mn), go);
+            red_max_u32_if(&p.minmax[2 * mm_clip + 1], __float_as_uint(mx), go);
+            mn = __int_as_float(0x7f800000);
+            mx = 0.f;
+        };
+
+        uint32_t slot = 0, phase = 0;
+        uint32_t zbits = 0;
+        int zb_clip = -1;
+        const size_t lane_off = size_t(lane) * p.T * p.C;          // out[b, m = lane + 32 r, t, c]
+        const size_t clip_elems = size_t(p.n_mel) * p.T * p.C;
+        for (int i = 0;; ++i) {
+            const TileBlock* tb = reinterpret_cast<const TileBlock*>(sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes);
+            // ---- gather + mix: v = sum over the stages of this tile of gain * frame ----
+            cpx v[16];
+            mbar_wait_backoff(&full[slot], phase, 32, 512);           // also publishes the TileBlock of this tile
+            const int4 hdr = *reinterpret_cast<const int4*>(tb);
+            const int n_st = hdr.x;
+            if (n_st == 0) break;                    // end marker
+            {
+                const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[0].j_lo);   // j_lo | j_cnt << 16, gain
+                const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
+                const float g0 = active ? __uint_as_float(dd.y) : 0.f;
+                const float2* src = reinterpret_cast<const float2*>(my_rows + slot * slotB);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 x = src[32 * q];
+                    v[q] = cpx{g0 * x.x, g0 * x.y};
+                }
+                __syncwarp();
+                mbar_arrive_if(&empty[slot], l0);
+                if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+            }
+            for (int e = 1; e < n_st; ++e) {
+                mbar_wait_backoff(&full[slot], phase, 32, 512);
+                const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[e].j_lo);
+                const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
+                if (active) {
+                    const float gn = __uint_as_float(dd.y);
+                    const float2* src = reinterpret_cast<const float2*>(my_rows + slot * slotB);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float2 x = src[32 * q];
+                        v[q].x = fmaf(gn, x.x, v[q].x);
+                        v[q].y = fmaf(gn, x.y, v[q].y);
+                    }
+                }
+                __syncwarp();
+                mbar_arrive_if(&empty[slot], l0);
+                if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+            }
+
+            const int b = hdr.y;
+            const int pair = hdr.z >> 24;
+            const int t = (hdr.z & 0xffffff) + j;
+            const bool in_range = t < p.T;
+            const bool has1 = (2 * pair + 1 < p.C);
+            // SpecAugment time mask of this frame (transforms.py:12-40), precomputed per tile
+            const float mt = ((uint32_t(hdr.w) >> j) & 1u) ? 0.f : 1.f;
+            // a fully time-masked frame has zero magnitude everywhere: no FFT needed for mel
+            const bool do_fft = in_range && !(kMel && mt == 0.f);
+
+            // per-lane bitmap of the bins zeroed by the frequency masks (transforms.py:12-40)
+            // and stft_filter (data_utils.py:126-136): bit jj -> bin k1 + 16 (2 jj + par),
+            // bit 8 -> bin 256.  Recomputed when the clip changes.
+            if (b != zb_clip) {
+                zb_clip = b;
+                zbits = 0;
+                const int4 fmv = *reinterpret_cast<const int4*>(tb->fm);
+                const int fmw[4] = {fmv.x, fmv.y, fmv.z, fmv.w};   // size | offset << 16
+#pragma unroll
+                for (int q = 0; q <= 4; ++q) {
+                    if (q < 4 && q >= p.n_fmask) continue;
+                    if (q == 4 && !kMel) continue;   // store_bin filters after the channel remap
+                    const int size = q < 4 ? (fmw[q] & 0xffff) : p.filter_k;
+                    const int off = q < 4 ? (fmw[q] >> 16) : 1;
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj)
+                        if (unsigned(k1 + 16 * (2 * jj + par) - off) < unsigned(size)) zbits |= 1u << jj;
+                    if (NJ == 8 && unsigned(256 - off) < unsigned(size)) zbits |= 1u << 8;
+                }
+            }
+
+            cpx u[16];
             if (do_fft) {
-                auto emit = [&](int f, cpx zf, cpx zm) {
-                    const unsigned fi = unsigned(f - f_lo);
-                    if (fi < unsigned(f_n)) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q].x *= w8[q];
+                    v[q].y *= w8[q];
+                    v[q + 8].x = fmaf(-w8[q], v[q + 8].x, v[q + 8].x);
+                    v[q + 8].y = fmaf(-w8[q], v[q + 8].y, v[q + 8].y);
+                }
+                warp_pass1(v, [&](int q, float& a, float& bb, float& c, float& d) {
+                    const float4 w = s_tw1[q * 32];
+                    a = w.x; bb = w.y; c = w.z; d = w.w;
+                });
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    *reinterpret_cast<float2*>(xch + xw_write_off(k, lane)) = make_float2(v[k].x, v[k].y);
+                __syncwarp();
+                const unsigned char* row = xch + xw_read_off(k1, 0);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float4 a = *reinterpret_cast<const float4*>(row + 16 * m);
+                    const float4 c = *reinterpret_cast<const float4*>(row + 16 * (m + 8));
+                    const float4 tw = s_ts[2 * m];
+                    u[2 * m] = warp_dif(cpx{a.x, a.y}, cpx{c.x, c.y}, sgn, tw.x, tw.y);
+                    u[2 * m + 1] = warp_dif(cpx{a.z, a.w}, cpx{c.z, c.w}, sgn, tw.z, tw.w);
+                }
+                Fft<16>::run(u);
+                __syncwarp();   // every lane is done with the exchange rows (reused for |X| below)
+            }
+
+            // ---- epilogue ----
+            // register jj holds bin f = k1 + 16 (2 jj + par); its mirror 512 - f is register
+            // 15 - jj of the partner lane (lane 0: its own register (16 - jj) & 15)
+            auto mirror = [&](int jj) -> cpx {
+                const cpx mine = l0 ? u[(16 - jj) & 15] : u[15 - jj];
+                return cpx{__shfl_sync(0xffffffffu, mine.x, partner), __shfl_sync(0xffffffffu, mine.y, partner)};
+            };
+            if (kMel) {
+                if (p.do_minmax && b != mm_clip) {
+                    if (mm_clip >= 0) flush_minmax();
+                    mm_clip = b;
+                }
+                float2* mg = reinterpret_cast<float2*>(xch);   // [mel_f_n] (|ch0|, |ch1|)
+                const int f_lo = p.mel_f_lo, f_n = p.mel_f_n;
+                float acc0[4], acc1[4];   // mel bins m = lane + 32 r
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+                if (do_fft) {   // warp-uniform
+                    auto emit = [&](int f, int bit, cpx zf, cpx zm) {
                         const float r0 = zf.x + zm.x, i0 = zf.y - zm.y;
                         const float r1 = zf.y + zm.y, i1 = zm.x - zf.x;
-                        mg[fi] = make_float2(sqrt_approx(fmaf(r0, r0, i0 * i0)),
-                                             sqrt_approx(fmaf(r1, r1, i1 * i1)));
-                    }
-                };
+                        float m0 = sqrt_approx(fmaf(r0, r0, i0 * i0));
+                        float m1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
+                        if ((zbits >> bit) & 1u) { m0 = 0.f; m1 = 0.f; }   // |x| * 0 == +0
+                        const unsigned fi = unsigned(f - f_lo);
+                        if (fi < unsigned(f_n)) mg[fi] = make_float2(m0, m1);
+                    };
 #pragma unroll
-                for (int k2 = 0; k2 < KB; ++k2) {
-                    const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
-                    const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
-                    emit(ka + 32 * k2, Za[k2], pa);
-                    emit(kb + 32 * k2, Zb[k2], pb);
-                }
-                if (KB == 8 && l0) emit(256, Za[8], Za[8]);
-                __syncwarp(hmask);
-                // frequency masks (transforms.py:12-40) and stft_filter (data_utils.py:126-136)
-                // zero whole bins: |x| * 0 == +0
-                if (p.n_fmask > 0 || p.filter_k > 0) {
-                    for (int i = 0; i <= p.n_fmask; ++i) {
-                        int off, size;
-                        if (i < p.n_fmask) { size = tb->fm[2 * i]; off = tb->fm[2 * i + 1]; }
-                        else { off = 1; size = p.filter_k; }
-                        for (int f = off + n2; f < off + size; f += 16) {
-                            const unsigned fi = unsigned(f - f_lo);
-                            if (fi < unsigned(f_n)) mg[fi] = make_float2(0.f, 0.f);
+                    for (int jj = 0; jj < NJ; ++jj) emit(k1 + 16 * (2 * jj + par), jj, u[jj], mirror(jj));
+                    if (NJ == 8) {
+                        const cpx z8 = u[8];
+                        if (l0) emit(256, 8, z8, z8);
+                    }
+                    __syncwarp();
+                    // sparse mel projection (transforms.py:51-77): filter m = lane + 32 r reads
+                    // mel_L[r] taps starting at its first bin; shorter filters are zero-padded,
+                    // so the trip count is uniform across the warp
+                    const float* wr = reinterpret_cast<const float*>(sm + OFF_MW) + lane;
+                    const uint32_t* ms = reinterpret_cast<const uint32_t*>(sm + OFF_MSTART) + lane;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 32); uniform
+                        if (L == 0) break;
+                        const float2* a = mg + ms[32 * r];
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int q = 0; q < kMaxFilter; q += 2) {   // L is even (iris_set_mel pads)
+                            if (q >= L) break;                        // uniform
+                            const float2 x0 = a[q], x1 = a[q + 1];
+                            const float w0 = wr[32 * q], w1 = wr[32 * q + 32];
+                            s0 = fmaf(w0, x0.x, s0);
+                            s1 = fmaf(w0, x0.y, s1);
+                            s0 = fmaf(w1, x1.x, s0);
+                            s1 = fmaf(w1, x1.y, s1);
                         }
+                        acc0[r] = s0;
+                        acc1[r] = s1;
+                        wr += 32 * L;
                     }
-                    __syncwarp(hmask);
+                    __syncwarp();   // mags are consumed before the next frame's exchange
                 }
-                // sparse mel projection (transforms.py:51-77): filter m = n2 + 16 r reads
-                // mel_L[r] taps starting at its first bin; shorter filters are zero-padded, so
-                // the trip count is uniform across the half-warp
-                const float* wr = s_mw + n2;
-#define IRIS_TAP(i)                                            \
-    {                                                          \
-        const float2 x = a[i];                                 \
-        const float w = wr[16 * (i)];                          \
-        acc0[r] = fmaf(w, x.x, acc0[r]);                       \
-        acc1[r] = fmaf(w, x.y, acc1[r]);                       \
-    }
+                // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
+                if (in_range) {
+                    const int C = p.C;
+                    float* o = p.out + size_t(b) * clip_elems + lane_off + size_t(t) * C + 2 * pair;
+                    const size_t rs32 = size_t(32) * p.T * C;
+                    const bool lg = p.do_log && !p.do_minmax;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 16); uniform
-                    const float2* a = mg + s_minfo[n2 + 16 * r];
-                    switch (L) {   // one uniform jump, then straight-line taps
-                        case 12: IRIS_TAP(11)
-                        case 11: IRIS_TAP(10)
-                        case 10: IRIS_TAP(9)
-                        case 9: IRIS_TAP(8)
-                        case 8: IRIS_TAP(7)
-                        case 7: IRIS_TAP(6)
-                        case 6: IRIS_TAP(5)
-                        case 5: IRIS_TAP(4)
-                        case 4: IRIS_TAP(3)
-                        case 3: IRIS_TAP(2)
-                        case 2: IRIS_TAP(1)
-                        case 1: IRIS_TAP(0)
-                        default: break;
+                    for (int r = 0; r < 4; ++r) {
+                        if (lane + 32 * r < p.n_mel) {
+                            float a0 = acc0[r], a1 = acc1[r];
+                            if (p.do_minmax) {
+                                mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
+                                mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
+                            }
+                            if (lg) {
+                                a0 = __logf(a0 + 1e-8f);
+                                a1 = __logf(a1 + 1e-8f);
+                            }
+                            if ((C & 1) == 0) {
+                                *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                            } else {
+                                o[0] = a0;
+                                if (has1) o[1] = a1;
+                            }
+                        }
+                        o += rs32;
                     }
-                    wr += 16 * L;
                 }
-#undef IRIS_TAP
-            }
-            // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
-            if (in_range) {
-                const int C = p.C;
-                float* o = p.out + (size_t(b) * p.n_mel * p.T + t) * C + 2 * pair + size_t(n2) * p.T * C;
-                const int rs16 = 16 * p.T * C;
-                const bool lg = p.do_log && !p.do_minmax;
-                const int n_r = (p.n_mel + 15) >> 4;
+            } else if (MODE == FM_ACTIVITY) {
+                // frame "active" iff any STFT coefficient (any bin, re or im, any channel) > 0
+                // (pipeline.py:55)
+                float mxv = 0.f;
+                if (do_fft) {
+                    auto emit = [&](cpx zf, cpx zm) {
+                        mxv = fmaxf(mxv, fmaxf(fmaxf(zf.x + zm.x, zf.y - zm.y),
+                                               fmaxf(zf.y + zm.y, zm.x - zf.x)));
+                    };
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (r >= n_r) break;                                  // uniform
-                    if (r == n_r - 1 && n2 + 16 * r >= p.n_mel) break;    // ragged last group
-                    float a0 = acc0[r], a1 = acc1[r];
-                    if (p.do_minmax) {
-                        mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
-                        mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
-                    }
-                    if (lg) {
-                        a0 = __logf(a0 + 1e-8f);
-                        a1 = __logf(a1 + 1e-8f);
-                    }
-                    if ((C & 1) == 0) {
-                        *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
-                    } else {
-                        o[0] = a0;
-                        if (has1) o[1] = a1;
-                    }
-                    o += rs16;
+                    for (int jj = 0; jj < 8; ++jj) emit(u[jj], mirror(jj));
+                    if (l0) emit(u[8], u[8]);
                 }
-            }
-        } else if (MODE == FM_ACTIVITY) {
-            // frame "active" iff any STFT coefficient (any bin, re or im, any channel) > 0
-            // (pipeline.py:55)
-            float mxv = 0.f;
-            if (do_fft) {
-                auto emit = [&](cpx zf, cpx zm) {
-                    mxv = fmaxf(mxv, fmaxf(fmaxf(zf.x + zm.x, zf.y - zm.y),
-                                           fmaxf(zf.y + zm.y, zm.x - zf.x)));
-                };
 #pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) {
-                    const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
-                    const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
-                    emit(Za[k2], pa);
-                    emit(Zb[k2], pb);
-                }
-                if (l0) emit(Za[8], Za[8]);
-            }
+                for (int o = 16; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
+                if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
+            } else if (do_fft) {
+                // stft_filter is applied by store_bin (it follows the channel remap)
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(hmask, mxv, o));
-            if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
-        } else if (do_fft) {
-            // per-lane bitmap of frequency-masked bins: bit k2 -> ka + 32*k2,
-            // bit 8 + k2 -> kb + 32*k2, bit 16 -> bin 256
-            uint32_t zbits = 0;
-            for (int i = 0; i < p.n_fmask; ++i) {
-                const int size = tb->fm[2 * i], off = tb->fm[2 * i + 1];
-#pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) {
-                    if (unsigned(ka + 32 * k2 - off) < unsigned(size)) zbits |= 1u << k2;
-                    if (unsigned(kb + 32 * k2 - off) < unsigned(size)) zbits |= 1u << (8 + k2);
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int f = k1 + 16 * (2 * jj + par);
+                    const cpx zf = u[jj], zm = mirror(jj);
+                    store_bin<MODE>(p, b, f, t, pair, has1, zf.x + zm.x, zf.y - zm.y, zf.y + zm.y,
+                                    zm.x - zf.x, ((zbits >> jj) & 1u) ? 0.f : mt);
                 }
-                if (unsigned(256 - off) < unsigned(size)) zbits |= 1u << 16;
-            }
-#pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) {
-                const cpx pa = l0 ? Za[(16 - k2) & 15] : Zb[15 - k2];
-                const cpx pb = l0 ? Zb[15 - k2] : Za[15 - k2];
-                {
-                    const int f = ka + 32 * k2;
-                    const cpx zf = Za[k2];
-                    store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pa.x, zf.y - pa.y,
-                                    zf.y + pa.y, pa.x - zf.x, ((zbits >> k2) & 1u) ? 0.f : mt);
+                if (l0) {
+                    const cpx zf = u[8];
+                    store_bin<MODE>(p, b, 256, t, pair, has1, zf.x + zf.x, zf.y - zf.y, zf.y + zf.y,
+                                    zf.x - zf.x, ((zbits >> 8) & 1u) ? 0.f : mt);
                 }
-                {
-                    const int f = kb + 32 * k2;
-                    const cpx zf = Zb[k2];
-                    store_bin<MODE>(p, b, f, t, pair, has1, zf.x + pb.x, zf.y - pb.y,
-                                    zf.y + pb.y, pb.x - zf.x, ((zbits >> (8 + k2)) & 1u) ? 0.f : mt);
-                }
-            }
-            if (l0) {
-                const cpx zf = Za[8];
-                store_bin<MODE>(p, b, 256, t, pair, has1, zf.x + zf.x, zf.y - zf.y,
-                                zf.y + zf.y, zf.x - zf.x, ((zbits >> 16) & 1u) ? 0.f : mt);
             }
         }
-        if (builder) {
-            fetch_block(k + 3, __shfl_sync(0xffffffffu, new_claim, 0));
-            fetch_done(k + 3);
-        }
-#ifndef IRIS_NO_TILE_BARRIER
-        // Not needed for correctness: keeps the 8 warps in the same phase, so that the slots are
-        // drained (and refilled) at the start of a tile and the loads fly during the FFTs.
-        // Measured on cfg2: 357 us with, 376 us without (COMPLEX: 457 vs 639 us).
-        __syncthreads();
-#endif
-    }
-    if (kMel && p.do_minmax && mm_clip >= 0) flush_minmax();
-    // the last CTA to leave resets the tile scheduler for the next launch
-    __syncthreads();
-    if (tid == 0) {
-        if (atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
-            p.sched[0] = 0u;
-            p.sched[1] = 0u;
-        }
+        if (kMel && p.do_minmax && mm_clip >= 0) flush_minmax();
     }
 }
 
-size_t fused_smem_bytes(const FusedParams& p, int) { return smem_total(p.np_shift); }
+size_t fused_smem_bytes(const FusedParams& p, int) { return smem_total(p.mel_taps, p.fr); }
 int fused_max_segments() { return kMaxStages; }
-int fused_max_mel_window() { return kXchSlotFloats / 2; }
 int fused_max_mel_taps() { return kMaxTaps; }
+int fused_max_mel_filter() { return kMaxFilter; }
+int fused_max_frames_per_tile() { return kMaxFR; }
+
+// Frames per tile = consumer warps per CTA.  FR = 8 (two CTAs of 8 + 1 warps per SM: the
+// consumer warps spread evenly over the 4 schedulers and two independent CTAs hide each
+// other's load waits) measured fastest on B200: cfg2 mel 216 us vs 228 us for FR = 16 x 1 CTA
+// and 271 us for FR = 20 at 80 registers (spills).  IRIS_FR overrides it for experiments.
+int fused_pick_fr(int T, int mel_taps) {
+    int want = 8;
+    if (const char* e = getenv("IRIS_FR")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxFR) want = v;
+    }
+    while (want > 1 && smem_total(mel_taps, want) > 227u * 1024u) --want;
+    (void)T;
+    return want;
+}
+
 size_t fused_tile_bytes(const FusedParams& p, int* stride_out) {
-    const int FR = 16 >> p.np_shift;
-    const long long n_tiles = (long long)p.B * p.n_groups * ((p.T + FR - 1) / FR);
+    const int FR = p.fr;
+    const long long n_tiles = (long long)p.B * p.n_pairs * ((p.T + FR - 1) / FR);
     int ms = p.max_segs < 1 ? 1 : p.max_segs;
-    const int stride = (32 + 24 * ms + 15) & ~15;
+    const int stride = 32 + 16 * ms;
     if (stride_out) *stride_out = stride;
     return size_t(n_tiles) * size_t(stride);
 }
 
-// p.tile_blocks (fused_tile_bytes) and p.sched (2 x uint32, zero) are provided by the caller.
+// p.tile_blocks (fused_tile_bytes) is provided by the caller.
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream) {
-    const int FR = 16 >> p.np_shift;
+    const int FR = p.fr;
+    if (FR < 1 || FR > kMaxFR) return cudaErrorInvalidValue;
     const int tpc = (p.T + FR - 1) / FR;
-    const long long n_tiles = (long long)p.B * p.n_groups * tpc;
+    const long long n_tiles = (long long)p.B * p.n_pairs * tpc;
     if (n_tiles <= 0) return cudaSuccess;
-    if (n_tiles > 0x7fffffffLL || p.max_segs > kMaxStages) return cudaErrorInvalidValue;
+    if (n_tiles > 0x7fffffffLL || p.max_segs > kMaxStages || p.n_pairs > 127) return cudaErrorInvalidValue;
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
-    const int grid = int(n_tiles < 2LL * num_sms ? n_tiles : 2LL * num_sms);
-#define IRIS_LAUNCH(M, KBV)                                                                     \
+    const int per_sm = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
+    const long long max_ctas = (long long)num_sms * per_sm;
+    const int grid = int(n_tiles < max_ctas ? n_tiles : max_ctas);
+    const int threads = (FR + 1) * 32;
+#define IRIS_LAUNCH(M, NJV)                                                                     \
     {                                                                                           \
         static bool attr_set = false;                                                           \
         if (!attr_set) {                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(k_fused<M, KBV>,                               \
+            cudaError_t e = cudaFuncSetAttribute(k_fused<M, NJV>,                               \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                                  227 * 1024);                                   \
             if (e != cudaSuccess) return e;                                                     \
-            cudaFuncSetAttribute(k_fused<M, KBV>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+            cudaFuncSetAttribute(k_fused<M, NJV>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                  cudaSharedmemCarveoutMaxShared);                               \
             attr_set = true;                                                                    \
         }                                                                                       \
-        k_fused<M, KBV><<<grid, kThreads, smem, stream>>>(p);                                   \
+        k_fused<M, NJV><<<grid, threads, smem, stream>>>(p);                                    \
     }
     switch (mode) {
         case FM_COMPLEX: IRIS_LAUNCH(FM_COMPLEX, 8) break;

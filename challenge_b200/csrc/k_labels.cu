@@ -9,33 +9,49 @@
 
 namespace iris {
 
+// Shared memory: the running frame labels L[T*K] (float) and the activity bytes of the
+// clip's voices act[V][T], gathered up front so that the sequential per-voice passes run from
+// shared memory (one global round trip per clip instead of two per voice).
 __global__ void __launch_bounds__(256) k_labels(const LabelParams p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.x;
     const int TK = p.T * p.K;
-    float* L = p.frame_labels + size_t(b) * TK;
+    float* L = reinterpret_cast<float*>(s_raw);                       // [T*K]
+    float* lab = L + TK;                                               // [V*K]
+    uint8_t* act = reinterpret_cast<uint8_t*>(lab + p.V * p.K);       // [V][T]
     __shared__ float s_max[8];
     __shared__ int s_keep;
-    for (int i = threadIdx.x; i < TK; i += blockDim.x) L[i] = 0.f;
     const int nv = p.n_voices[b];
+    for (int i = threadIdx.x; i < TK; i += blockDim.x) L[i] = 0.f;
+    for (int i = threadIdx.x; i < p.V * p.T; i += blockDim.x) {
+        const int v = i / p.T, t = i - v * p.T;
+        uint8_t a = 0;
+        if (v < nv) {
+            const int id = p.voice_id[size_t(b) * p.V + v];
+            const int k = t + p.voice_shift[size_t(b) * p.V + v];
+            if (k >= 0 && k < p.n_frames[id]) a = p.activity[size_t(id) * p.act_stride + k];
+        }
+        act[i] = a;
+    }
+    for (int i = threadIdx.x; i < p.V * p.K; i += blockDim.x) {
+        const int v = i / p.K;
+        lab[i] = v < nv ? p.bank_labels[size_t(p.voice_id[size_t(b) * p.V + v]) * p.K + (i - v * p.K)] : 0.f;
+    }
+    __syncthreads();
     for (int v = 0; v < p.V; ++v) {
         float* lv = p.labels_vtk ? p.labels_vtk + (size_t(b) * p.V + v) * TK : nullptr;
-        if (v >= nv) {
+        if (v >= nv) {   // uniform
             if (lv) for (int i = threadIdx.x; i < TK; i += blockDim.x) lv[i] = 0.f;
             if (threadIdx.x == 0) p.keep[size_t(b) * p.V + v] = 0;
             continue;
         }
-        const int id = p.voice_id[size_t(b) * p.V + v];
-        const int shift = p.voice_shift[size_t(b) * p.V + v];
-        const int kT = p.n_frames[id];
-        const uint8_t* act = p.activity + size_t(id) * p.act_stride;
-        const float* lab = p.bank_labels + size_t(id) * p.K;
+        const uint8_t* av = act + v * p.T;
+        const float* lb = lab + v * p.K;
         // max over (t, c) of (sum of accepted labels + candidate)   (pipeline.py:78)
         float mx = 0.f;
         for (int i = threadIdx.x; i < TK; i += blockDim.x) {
             const int t = i / p.K, c = i - t * p.K;
-            const int k = t + shift;
-            const float a = (k >= 0 && k < kT && act[k]) ? 1.f : 0.f;
-            mx = fmaxf(mx, L[i] + lab[c] * a);
+            mx = fmaxf(mx, L[i] + lb[c] * (av[t] ? 1.f : 0.f));
         }
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
@@ -50,19 +66,27 @@ __global__ void __launch_bounds__(256) k_labels(const LabelParams p) {
         const float keep = s_keep ? 1.f : 0.f;
         for (int i = threadIdx.x; i < TK; i += blockDim.x) {
             const int t = i / p.K, c = i - t * p.K;
-            const int k = t + shift;
-            const float a = (k >= 0 && k < kT && act[k]) ? 1.f : 0.f;
-            const float cand = lab[c] * a * keep;              // l * no_overlap (pipeline.py:84)
+            const float cand = lb[c] * (av[t] ? 1.f : 0.f) * keep;   // l * no_overlap (pipeline.py:84)
             L[i] += cand;
             if (lv) lv[i] = cand;
         }
         __syncthreads();
     }
+    float* out = p.frame_labels + size_t(b) * TK;
+    for (int i = threadIdx.x; i < TK; i += blockDim.x) out[i] = L[i];
 }
 
 cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream) {
     if (p.B <= 0) return cudaSuccess;
-    k_labels<<<p.B, 256, 0, stream>>>(p);
+    const size_t smem = (size_t(p.T) * p.K + size_t(p.V) * p.K) * 4 + size_t(p.V) * p.T;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_labels<<<p.B, 256, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -127,6 +127,20 @@ def test_fftcore_math_on_host(tmp_path):
     assert r['im_dc'] == 0.0 and r['im_nyq'] == 0.0
 
 
+def test_fftwarp_math_on_host(tmp_path):
+    """fftwarp.cuh (the warp-per-frame FFT of the fused kernel) compiled with g++: 32 emulated
+    lanes, the exchange offsets, the DIF + partner/mirror maps and the two-channel split
+    reproduce a float64 windowed DFT; bins < 128 need only half of pass 2's outputs."""
+    exe = str(tmp_path / 'fftwarp_host')
+    subprocess.check_call(['g++', '-std=c++17', '-O2', '-x', 'c++', '-I',
+                           os.path.join(ROOT, 'challenge_b200', 'csrc'),
+                           os.path.join(ROOT, 'tests', 'host', 'fftwarp_host.cpp'), '-o', exe])
+    r = json.loads(subprocess.check_output([exe]).decode())
+    assert r['bad_map'] == 0 and r['missing'] == 0 and r['bad_prune'] == 0
+    assert r['err512'] / r['max_abs'] < 1e-6
+    assert r['im_dc'] == 0.0 and r['im_nyq'] == 0.0
+
+
 def test_default_mel_matrix_is_the_tf_restatement():
     from challenge_b200.engine import default_mel_matrix
     from oracle.transforms import linear_to_mel_weight_matrix
