@@ -62,7 +62,7 @@ struct FusedParams {
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
     int32_t do_log, do_minmax;
-    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); k_logmel_post re-zeroes it
+    uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); zeroed by k_tiles
     // mel projection: filters are handled in rounds of 32 (m = lane + 32 r); every filter of
     // round r reads mel_L[r] consecutive magnitudes starting at bin mel_f_lo + mel_info[m]
     // (shorter filters are zero-padded), weights at mel_w[(row0(r) + i) * 32 + lane]

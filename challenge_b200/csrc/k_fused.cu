@@ -95,10 +95,17 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
     const int per_clip = tpc * p.n_pairs;
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= p.B * per_clip) return;
+    if (tile < p.B && p.minmax != nullptr) {   // per-clip extrema scratch of the launch that follows
+        p.minmax[2 * tile] = 0u;
+        p.minmax[2 * tile + 1] = 0u;
+    }
+    // tile order: clip, then time, then channel pair -- the pairs of one (clip, time) range are
+    // consecutive tiles (same work chunk), so the partial sectors they write to the same
+    // out[b, f, t, :] rows merge in L2 within microseconds
     const int b = tile / per_clip;
     const int r = tile - b * per_clip;
-    const int pair = r / tpc;
-    const int t0 = (r - pair * tpc) * FR;
+    const int pair = r % p.n_pairs;
+    const int t0 = (r / p.n_pairs) * FR;
     const int t_end = min(t0 + FR, p.T);
     unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
     StageDesc* d = reinterpret_cast<StageDesc*>(blk + 32);

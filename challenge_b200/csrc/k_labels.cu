@@ -23,15 +23,18 @@ __global__ void __launch_bounds__(256) k_labels(const LabelParams p) {
     __shared__ int s_keep;
     const int nv = p.n_voices[b];
     for (int i = threadIdx.x; i < TK; i += blockDim.x) L[i] = 0.f;
-    for (int i = threadIdx.x; i < p.V * p.T; i += blockDim.x) {
-        const int v = i / p.T, t = i - v * p.T;
-        uint8_t a = 0;
+    for (int v = 0; v < p.V; ++v) {
+        int id = 0, shift = 0, kT = 0;
         if (v < nv) {
-            const int id = p.voice_id[size_t(b) * p.V + v];
-            const int k = t + p.voice_shift[size_t(b) * p.V + v];
-            if (k >= 0 && k < p.n_frames[id]) a = p.activity[size_t(id) * p.act_stride + k];
+            id = p.voice_id[size_t(b) * p.V + v];
+            shift = p.voice_shift[size_t(b) * p.V + v];
+            kT = p.n_frames[id];
         }
-        act[i] = a;
+        const uint8_t* src = p.activity + size_t(id) * p.act_stride;
+        for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+            const int k = t + shift;
+            act[v * p.T + t] = (k >= 0 && k < kT) ? src[k] : uint8_t(0);
+        }
     }
     for (int i = threadIdx.x; i < p.V * p.K; i += blockDim.x) {
         const int v = i / p.K;
@@ -49,9 +52,9 @@ __global__ void __launch_bounds__(256) k_labels(const LabelParams p) {
         const float* lb = lab + v * p.K;
         // max over (t, c) of (sum of accepted labels + candidate)   (pipeline.py:78)
         float mx = 0.f;
-        for (int i = threadIdx.x; i < TK; i += blockDim.x) {
-            const int t = i / p.K, c = i - t * p.K;
-            mx = fmaxf(mx, L[i] + lb[c] * (av[t] ? 1.f : 0.f));
+        for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+            const float a = av[t] ? 1.f : 0.f;
+            for (int c = 0; c < p.K; ++c) mx = fmaxf(mx, L[t * p.K + c] + lb[c] * a);
         }
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
@@ -64,11 +67,13 @@ __global__ void __launch_bounds__(256) k_labels(const LabelParams p) {
         }
         __syncthreads();
         const float keep = s_keep ? 1.f : 0.f;
-        for (int i = threadIdx.x; i < TK; i += blockDim.x) {
-            const int t = i / p.K, c = i - t * p.K;
-            const float cand = lb[c] * (av[t] ? 1.f : 0.f) * keep;   // l * no_overlap (pipeline.py:84)
-            L[i] += cand;
-            if (lv) lv[i] = cand;
+        for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+            const float a = av[t] ? 1.f : 0.f;
+            for (int c = 0; c < p.K; ++c) {
+                const float cand = lb[c] * a * keep;              // l * no_overlap (pipeline.py:84)
+                L[t * p.K + c] += cand;
+                if (lv) lv[t * p.K + c] = cand;
+            }
         }
         __syncthreads();
     }
