@@ -112,16 +112,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// wait with exponential back-off: a warp that polls in a tight loop takes issue slots from
-// the warps that have work; the first polls stay quick because data is usually about to land
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns0,
-                                                  unsigned ns_max) {
-    if (mbar_try_wait(bar, parity)) return;
-    unsigned ns = ns0;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(ns);
-        ns = min(2u * ns, ns_max);
-    }
+// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware until the phase
+// completes (or ~10 ms pass), so a waiting warp issues next to nothing.  __nanosleep-based
+// back-off measured ~15 ns per poll on B200 (170 wasted instructions per frame); this form is
+// what CUTLASS' ClusterBarrier::wait uses.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "IRIS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra IRIS_DONE_%=;\n\t"
+        "bra IRIS_WAIT_%=;\n\t"
+        "IRIS_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 // arrive from the lanes where `pred` holds, as ONE predicated instruction (an `if` around
 // mbar_arrive splits the warp until the next reconvergence point)

@@ -292,8 +292,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 const TileBlock* tb = reinterpret_cast<const TileBlock*>(ent);
                 for (int s = 0; s < n; ++s) {
                     // the whole warp waits (one instruction per poll either way) so that it stays
-                    // converged; polls back off because a slot frees up once per ~microsecond
-                    mbar_wait_backoff(&empty[slot], phase ^ 1u, 128, 512);
+                    // converged
+                    mbar_wait_parked(&empty[slot], phase ^ 1u);
                     if (lane == 0) {
                         const StageDesc d = tb->d[s];
                         if (d.j_cnt == 0) {
@@ -313,7 +313,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
             if (lane == 0) *reinterpret_cast<int4*>(ent) = make_int4(0, 0, 0, 0);
             __syncwarp();
-            mbar_wait_backoff(&empty[slot], phase ^ 1u, 128, 512);
+            mbar_wait_parked(&empty[slot], phase ^ 1u);
             if (lane == 0) {
                 mbar_arrive(&full[slot]);
                 // the last CTA to get here resets the work counter for the next launch
@@ -362,7 +362,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             const TileBlock* tb = reinterpret_cast<const TileBlock*>(sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes);
             // ---- gather + mix: v = sum over the stages of this tile of gain * frame ----
             cpx v[16];
-            mbar_wait_backoff(&full[slot], phase, 32, 512);           // also publishes the TileBlock of this tile
+            mbar_wait_parked(&full[slot], phase);           // also publishes the TileBlock of this tile
             const int4 hdr = *reinterpret_cast<const int4*>(tb);
             const int n_st = hdr.x;
             if (n_st == 0) break;                    // end marker
@@ -381,7 +381,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 if (++slot == kSlots) { slot = 0; phase ^= 1u; }
             }
             for (int e = 1; e < n_st; ++e) {
-                mbar_wait_backoff(&full[slot], phase, 32, 512);
+                mbar_wait_parked(&full[slot], phase);
                 const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[e].j_lo);
                 const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
                 if (active) {
