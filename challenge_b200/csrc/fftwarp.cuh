@@ -4,7 +4,7 @@
 //   pass 1 (registers):  A[n2][k1] = sum_i x[n2 + 32 i] W16^(i k1)          (16-point FFT)
 //   twiddle:             B[n2][k1] = A[n2][k1] * W512^(n2 k1)
 //   exchange (shared):   row k1 holds B[.][k1] for all 32 n2
-//   pass 2 (registers):  lane L = 2*k1 + p computes the outputs k2 = 2j + p of the 32-point
+//   pass 2 (registers):  lane L = k1 + 16*p computes the outputs k2 = 2j + p of the 32-point
 //                        FFT of its row by one radix-2 DIF step + a 16-point FFT:
 //                          u[i] = (B[i] + s*B[i+16]) * (p ? W32^i : 1),  s = p ? -1 : +1
 //                          Y[j] = sum_i u[i] W16^(i j) = X[k1 + 16*(2j + p)]
@@ -30,12 +30,16 @@ constexpr int kXwBytes = 16 * kXwRowBytes;        // 4352 per warp
 IRIS_HD int xw_write_off(int k1, int n2) { return k1 * kXwRowBytes + n2 * 8; }        // float2
 IRIS_HD int xw_read_off(int k1, int m) { return k1 * kXwRowBytes + m * 16; }          // float4 {B[2m], B[2m+1]}
 
-IRIS_HD int warp_k1(int lane) { return lane >> 1; }
-IRIS_HD int warp_par(int lane) { return lane & 1; }
+// lane L = k1 + 16 * par: the 16 lanes of a half-warp hold 16 consecutive bins, so that the
+// shared-memory rows a quarter-warp touches are distinct (conflict-free 128-bit accesses)
+IRIS_HD int warp_k1(int lane) { return lane & 15; }
+IRIS_HD int warp_par(int lane) { return lane >> 4; }
 // bin held by register j of a lane after pass 2
-IRIS_HD int warp_bin(int lane, int j) { return (lane >> 1) + 16 * (2 * j + (lane & 1)); }
+IRIS_HD int warp_bin(int lane, int j) { return (lane & 15) + 16 * (2 * j + (lane >> 4)); }
 // lane holding the mirror bins of this lane
-IRIS_HD int warp_partner(int lane) { return lane < 2 ? lane : 2 * (16 - (lane >> 1)) + (1 - (lane & 1)); }
+IRIS_HD int warp_partner(int lane) {
+    return (lane & 15) == 0 ? lane : (16 - (lane & 15)) + 16 * (1 - (lane >> 4));
+}
 // register of the partner that holds the mirror of own register j
 IRIS_HD int warp_mirror_reg(int lane, int j) { return lane == 0 ? ((16 - j) & 15) : 15 - j; }
 

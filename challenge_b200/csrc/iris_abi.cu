@@ -123,6 +123,7 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
 // tile-block scratch of a launch, then k_tiles + k_fused
 int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
     p.max_segs = max_segs < 1 ? 1 : max_segs;
+    p.stage_out = fused_stages_output(mode, p.remap, p.fr) && !getenv("IRIS_NO_STAGE") ? 1 : 0;
     int stride = 0;
     const size_t bytes = fused_tile_bytes(p, &stride);
     CU(c->tiles.reserve(bytes));

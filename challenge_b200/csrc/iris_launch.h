@@ -10,6 +10,7 @@ struct FusedParams;
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
 int fused_max_segments();      // mixing segments one clip may have
+bool fused_stages_output(int mode, int remap, int fr);   // FusedParams::stage_out for a launch
 int fused_max_mel_taps();      // sum over the 32-filter rounds of the longest filter
 int fused_max_mel_filter();    // taps of the longest filter
 int fused_max_frames_per_tile();

@@ -19,7 +19,7 @@
 //  * Tiles are claimed in chunks of consecutive tiles from a global counter.  The producer warp
 //    copies the TileBlock of each tile into a shared-memory descriptor ring and fetches every
 //    stage -- (j_cnt + 1) contiguous 2 KB rows of the pair-interleaved bank -- with ONE
-//    cp.async.bulk (TMA 1-D) into a ring of kSlots stage buffers: full[slot] completes when
+//    cp.async.bulk (TMA 1-D) into a ring of 3 (mel) or 2 (spectrogram modes) stage buffers: full[slot] completes when
 //    the bytes have landed, empty[slot] when all FR consumer warps have read the slot.
 //  * Consumer warps never synchronise with each other: each waits on full[slot], accumulates
 //    gain * frame into its 16 complex registers per lane, releases the slot, and after the
@@ -35,8 +35,7 @@
 
 namespace iris {
 
-constexpr int kSlots = 3;        // stage buffers per CTA
-constexpr int kRing = 8;         // TileBlock ring entries (> kSlots + 1, see the producer)
+constexpr int kRing = 8;         // TileBlock ring entries (> stage buffers + 1, see the producer)
 constexpr int kMaxStages = 16;   // mixing segments of one clip (upper bound on stages per tile)
 #ifndef IRIS_MAX_FR
 #define IRIS_MAX_FR 16
@@ -68,8 +67,8 @@ static_assert(sizeof(TileBlock) == 32 + 16 * kMaxStages, "TileBlock layout");
 constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
 // ---- shared memory map (bytes) ----
-constexpr int OFF_FULL = 0;                                  // uint64 full[kSlots]
-constexpr int OFF_EMPTY = 32;                                // uint64 empty[kSlots]
+constexpr int OFF_FULL = 0;                                  // uint64 full[<= 3]
+constexpr int OFF_EMPTY = 32;                                // uint64 empty[<= 3]
 constexpr int OFF_RING = 64;
 constexpr int OFF_TW1 = OFF_RING + kRing * kTileBlockBytes;  // float4 [8][32]
 constexpr int OFF_TS = OFF_TW1 + 8 * 32 * 16;                // float4 [8][2]
@@ -84,8 +83,19 @@ __host__ __device__ inline uint32_t off_slots(int mel_taps, int fr) {
     return off_xch(mel_taps) + uint32_t(fr) * uint32_t(kXwBytes);   // kXwBytes % 128 == 0
 }
 __host__ __device__ inline uint32_t slot_bytes(int fr) { return uint32_t(fr + 1) * 2048u; }
-__host__ __device__ inline uint32_t smem_total(int mel_taps, int fr) {
-    return off_slots(mel_taps, fr) + kSlots * slot_bytes(fr);
+// stage buffers per CTA: the modes that write whole spectrograms trade one stage buffer for
+// the store staging area below
+__host__ __device__ constexpr int slots_of(int mode) { return (mode == FM_MEL || mode == FM_ACTIVITY) ? 3 : 2; }
+// staging of a tile's [257 bins][FR frames] x 16 B output pieces (16-byte columns XOR-swizzled
+// by the bin so that both the per-frame writes and the per-bin reads are conflict-free)
+__host__ __device__ inline uint32_t stage_bytes(int fr) { return uint32_t(kBins) * uint32_t(fr) * 16u; }
+__host__ __device__ inline uint32_t smem_total(int mel_taps, int fr, int mode, bool staged) {
+    return off_slots(mel_taps, fr) + slots_of(mode) * slot_bytes(fr) + (staged ? stage_bytes(fr) : 0u);
+}
+// spectrogram modes without a channel remap (16 B per (bin, frame, pair)) store through the
+// staging area; 8 frames per tile give 128-byte rows
+__host__ __device__ inline bool stages_output(int mode, int remap, int fr) {
+    return mode != FM_MEL && mode != FM_ACTIVITY && remap == REMAP_NONE && fr == 8;
 }
 
 // ---- pre-kernel: one thread per tile builds its TileBlock ----
@@ -154,6 +164,49 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
     *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
 }
 
+// one (bin, frame, channel pair) of the spectrogram modes without a channel remap:
+// {first-half ch0, ch1, second-half ch0, ch1} = (re, re, im, im) or (|.|, |.|, phase, phase)
+template <int MODE>
+__device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float r0, float i0, float r1,
+                                             float i1, float m) {
+    // masks are applied by multiplication (transforms.py:40) so zeros keep their sign
+    r0 *= m; i0 *= m; r1 *= m; i1 *= m;
+    if (p.filter_k > 0) {                                          // data_utils.py:126-136
+        const float filt = (f >= 1 && f <= p.filter_k) ? 0.f : 1.f;
+        r0 *= filt; i0 *= filt; r1 *= filt; i1 *= filt;
+    }
+    float a0 = r0, a1 = r1, b0 = i0, b1 = i1;
+    if (MODE != FM_COMPLEX) {
+        a0 = sqrt_approx(fmaf(r0, r0, i0 * i0));   // transforms.py:116
+        b0 = fast_atan2f(i0, r0);                  // transforms.py:117
+        a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
+        b1 = fast_atan2f(i1, r1);
+        if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
+            a0 = logf(a0 + 1e-8f);
+            a1 = logf(a1 + 1e-8f);
+        }
+    }
+    return make_float4(a0, a1, b0, b1);
+}
+__device__ __forceinline__ void store_piece(const FusedParams& p, int b, int f, int t, int pair, bool has1,
+                                            float4 v) {
+    const int C = p.C;
+    float* o = p.out + ((size_t(b) * kBins + f) * p.T + t) * size_t(2 * C);
+    if (C == 2) {
+        *reinterpret_cast<float4*>(o) = v;
+    } else if (has1 && (C & 1) == 0) {
+        *reinterpret_cast<float2*>(o + 2 * pair) = make_float2(v.x, v.y);
+        *reinterpret_cast<float2*>(o + C + 2 * pair) = make_float2(v.z, v.w);
+    } else {
+        o[2 * pair] = v.x;
+        o[C + 2 * pair] = v.z;
+        if (has1) {
+            o[2 * pair + 1] = v.y;
+            o[C + 2 * pair + 1] = v.w;
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, int t, int pair,
                                           bool has1, float r0, float i0, float r1, float i1,
@@ -167,10 +220,10 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
         if (p.filter_k > 0) { r0 *= filt; i0 *= filt; r1 *= filt; i1 *= filt; }
         float a0 = r0, a1 = r1, b0 = i0, b1 = i1;   // first half / second half of the last dim
         if (MODE != FM_COMPLEX) {
-            a0 = sqrtf(r0 * r0 + i0 * i0);           // transforms.py:116
-            b0 = atan2f(i0, r0);                     // transforms.py:117
-            a1 = sqrtf(r1 * r1 + i1 * i1);
-            b1 = atan2f(i1, r1);
+            a0 = sqrt_approx(fmaf(r0, r0, i0 * i0));   // transforms.py:116
+            b0 = fast_atan2f(i0, r0);                  // transforms.py:117
+            a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
+            b1 = fast_atan2f(i1, r1);
             if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
                 a0 = logf(a0 + 1e-8f);
                 a1 = logf(a1 + 1e-8f);
@@ -207,8 +260,8 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
             if (p.filter_k > 0) { re *= filt; im *= filt; }
             float a = re, ph = im;
             if (MODE != FM_COMPLEX) {
-                a = sqrtf(re * re + im * im);
-                ph = atan2f(im, re);
+                a = sqrt_approx(fmaf(re, re, im * im));
+                ph = fast_atan2f(im, re);
                 if (MODE == FM_LOGMAGPHASE) a = logf(a + 1e-8f);
             }
             o[c] = a;
@@ -223,6 +276,7 @@ template <int MODE, int NJ>
 __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr bool kMel = (MODE == FM_MEL);
+    constexpr int S = slots_of(MODE);      // stage buffers
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int FR = p.fr;
@@ -247,9 +301,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // rows of a slot outside a stage's frame range are read (and multiplied by 0) by the
         // frames the stage does not cover: they must hold finite numbers
         float4* z = reinterpret_cast<float4*>(slots);
-        for (uint32_t i = tid; i < kSlots * slotB / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t i = tid; i < S * slotB / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid == 0) {
-            for (int s = 0; s < kSlots; ++s) {
+            for (int s = 0; s < S; ++s) {
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], uint32_t(FR));
             }
@@ -261,9 +315,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 
     if (warp == FR) {
         // =========================== producer warp ===========================
-        // The producer is at most kSlots stages ahead of the slowest consumer and every tile
+        // The producer is at most S stages ahead of the slowest consumer and every tile
         // has at least one stage, so when it writes ring entry i the slowest consumer is
-        // still in tile >= i - kSlots - 1: kRing > kSlots + 1 entries never collide.
+        // still in tile >= i - S - 1: kRing > S + 1 entries never collide.
         // Work is claimed in chunks of p.chunk consecutive tiles from a global counter (the
         // next claim is issued one chunk ahead, so its latency is hidden): consecutive tiles of
         // a clip mostly stay on one SM (per-clip state changes rarely, the row shared by two
@@ -304,7 +358,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                             bulk_g2s(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot]);
                         }
                     }
-                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                    if (++slot == S) { slot = 0; phase ^= 1u; }
                 }
             }
         }
@@ -378,7 +432,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 }
                 __syncwarp();
                 mbar_arrive_if(&empty[slot], l0);
-                if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                if (++slot == S) { slot = 0; phase ^= 1u; }
             }
             for (int e = 1; e < n_st; ++e) {
                 mbar_wait_parked(&full[slot], phase);
@@ -396,7 +450,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 }
                 __syncwarp();
                 mbar_arrive_if(&empty[slot], l0);
-                if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                if (++slot == S) { slot = 0; phase ^= 1u; }
             }
 
             const int b = hdr.y;
@@ -565,8 +619,37 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
                 if (in_range && l0 && mxv > 0.f) p.activity[size_t(b) * p.T + t] = 1;
+            } else if (p.stage_out) {
+                // ---- spectrogram modes: every warp parks the 257 x 16 B pieces of its frame in
+                // the staging area, then the 8 warps store bin rows of 8 frames = 128 B each ----
+                float4* stg = reinterpret_cast<float4*>(slots + S * slotB);
+                if (do_fft) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int f = k1 + 16 * (2 * jj + par);
+                        const cpx zf = u[jj], zm = mirror(jj);
+                        stg[f * FR + (j ^ (f & 7))] =
+                            make_piece<MODE>(p, f, zf.x + zm.x, zf.y - zm.y, zf.y + zm.y, zm.x - zf.x,
+                                             ((zbits >> jj) & 1u) ? 0.f : mt);
+                    }
+                    if (l0) {
+                        const cpx zf = u[8];
+                        stg[256 * FR + j] = make_piece<MODE>(p, 256, zf.x + zf.x, zf.y - zf.y, zf.y + zf.y,
+                                                             zf.x - zf.x, ((zbits >> 8) & 1u) ? 0.f : mt);
+                    }
+                }
+                named_bar_sync(1, FR * 32);
+                {
+                    const int jt = lane & 7;                       // frame of the tile
+                    const int tt = (hdr.z & 0xffffff) + jt;
+                    if (tt < p.T) {
+                        for (int f = warp * 4 + (lane >> 3); f < kBins; f += FR * 4)
+                            store_piece(p, b, f, tt, pair, has1, stg[f * FR + (jt ^ (f & 7))]);
+                    }
+                }
+                named_bar_sync(1, FR * 32);   // the pieces are read before the next tile overwrites them
             } else if (do_fft) {
-                // stft_filter is applied by store_bin (it follows the channel remap)
+                // channel remaps: stft_filter is applied by store_bin (it follows the remap)
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                     const int f = k1 + 16 * (2 * jj + par);
@@ -585,8 +668,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     }
 }
 
-size_t fused_smem_bytes(const FusedParams& p, int) { return smem_total(p.mel_taps, p.fr); }
+size_t fused_smem_bytes(const FusedParams& p, int mode) { return smem_total(p.mel_taps, p.fr, mode, p.stage_out != 0); }
 int fused_max_segments() { return kMaxStages; }
+bool fused_stages_output(int mode, int remap, int fr) { return stages_output(mode, remap, fr); }
 int fused_max_mel_taps() { return kMaxTaps; }
 int fused_max_mel_filter() { return kMaxFilter; }
 int fused_max_frames_per_tile() { return kMaxFR; }
@@ -601,7 +685,7 @@ int fused_pick_fr(int T, int mel_taps) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxFR) want = v;
     }
-    while (want > 1 && smem_total(mel_taps, want) > 227u * 1024u) --want;
+    while (want > 1 && smem_total(mel_taps, want, FM_MEL, false) > 227u * 1024u) --want;
     (void)T;
     return want;
 }
