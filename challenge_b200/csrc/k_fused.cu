@@ -166,6 +166,21 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
 
 // one (bin, frame, channel pair) of the spectrogram modes without a channel remap:
 // {first-half ch0, ch1, second-half ch0, ch1} = (re, re, im, im) or (|.|, |.|, phase, phase)
+// W32^(2m), W32^(2m+1) as (cos, sin) of -2 pi i / 32, handed to f as compile-time constants
+template <class F>
+__device__ __forceinline__ void constexpr_for_pair(int m, F f) {
+    switch (m) {   // m is a constant of an unrolled loop: the switch folds away
+        case 0: f(1.f, 0.f, float(cx_cos2pi(1, 32)), -float(cx_sin2pi(1, 32))); break;
+        case 1: f(float(cx_cos2pi(2, 32)), -float(cx_sin2pi(2, 32)), float(cx_cos2pi(3, 32)), -float(cx_sin2pi(3, 32))); break;
+        case 2: f(float(cx_cos2pi(4, 32)), -float(cx_sin2pi(4, 32)), float(cx_cos2pi(5, 32)), -float(cx_sin2pi(5, 32))); break;
+        case 3: f(float(cx_cos2pi(6, 32)), -float(cx_sin2pi(6, 32)), float(cx_cos2pi(7, 32)), -float(cx_sin2pi(7, 32))); break;
+        case 4: f(float(cx_cos2pi(8, 32)), -float(cx_sin2pi(8, 32)), float(cx_cos2pi(9, 32)), -float(cx_sin2pi(9, 32))); break;
+        case 5: f(float(cx_cos2pi(10, 32)), -float(cx_sin2pi(10, 32)), float(cx_cos2pi(11, 32)), -float(cx_sin2pi(11, 32))); break;
+        case 6: f(float(cx_cos2pi(12, 32)), -float(cx_sin2pi(12, 32)), float(cx_cos2pi(13, 32)), -float(cx_sin2pi(13, 32))); break;
+        default: f(float(cx_cos2pi(14, 32)), -float(cx_sin2pi(14, 32)), float(cx_cos2pi(15, 32)), -float(cx_sin2pi(15, 32))); break;
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float r0, float i0, float r1,
                                              float i1, float m) {
@@ -502,13 +517,18 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                     *reinterpret_cast<float2*>(xch + xw_write_off(k, lane)) = make_float2(v[k].x, v[k].y);
                 __syncwarp();
                 const unsigned char* row = xch + xw_read_off(k1, 0);
+                // DIF twiddles t(i) = par ? W32^i : 1 selected from compile-time constants (a
+                // table in shared memory would cost 32 wavefronts per frame for 256 bytes)
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     const float4 a = *reinterpret_cast<const float4*>(row + 16 * m);
                     const float4 c = *reinterpret_cast<const float4*>(row + 16 * (m + 8));
-                    const float4 tw = s_ts[2 * m];
-                    u[2 * m] = warp_dif(cpx{a.x, a.y}, cpx{c.x, c.y}, sgn, tw.x, tw.y);
-                    u[2 * m + 1] = warp_dif(cpx{a.z, a.w}, cpx{c.z, c.w}, sgn, tw.z, tw.w);
+                    constexpr_for_pair(m, [&](float c0, float s0, float c1, float s1) {
+                        const float tx0 = par ? c0 : 1.f, ty0 = par ? s0 : 0.f;
+                        const float tx1 = par ? c1 : 1.f, ty1 = par ? s1 : 0.f;
+                        u[2 * m] = warp_dif(cpx{a.x, a.y}, cpx{c.x, c.y}, sgn, tx0, ty0);
+                        u[2 * m + 1] = warp_dif(cpx{a.z, a.w}, cpx{c.z, c.w}, sgn, tx1, ty1);
+                    });
                 }
                 Fft<16>::run(u);
                 __syncwarp();   // every lane is done with the exchange rows (reused for |X| below)
