@@ -298,13 +298,26 @@ def run_gpu_arm(args):
     counts = torch.zeros((n_all + n_e2e_all + 1, 6), dtype=torch.int64, device=dev)
     KERNELS = ['k_labels', 'k_tiles', 'k_fused<FM_MEL>', 'k_logmel_post', 'k_metric_counts']
 
+    side = torch.cuda.Stream(device=dev)
+    ev_lab = torch.cuda.Event()
+    ev_met = torch.cuda.Event()
+
     def device_step(i, out):
-        """labels + fused features + metric counts (+ count all-reduce) on the current stream."""
+        """labels -> {fused features  ||  metric counts (+ count all-reduce)}: the counting only
+        needs the frame labels, so it runs on a second stream beside the feature kernel and
+        the step ends when both are done."""
+        main = torch.cuda.current_stream()
         frame, _, _ = eng.labels(want_keep=False)
+        ev_lab.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_lab)
+            eng.metric_counts(frame, y_pred, counts=counts[i], want_er=False)
+            if world > 1:
+                dist.all_reduce(counts[i])                  # NCCL sum of the int64 count vector
+            ev_met.record(side)
+            frame.record_stream(side)
         eng.features(L.FEAT_LOGMEL_MINMAX, out=out)
-        eng.metric_counts(frame, y_pred, counts=counts[i], want_er=False)
-        if world > 1:
-            dist.all_reduce(counts[i])                      # NCCL sum of the int64 count vector
+        main.wait_event(ev_met)
         return frame
 
     # ---- kernel-resident timing: plan already uploaded, CUDA events per step ----
