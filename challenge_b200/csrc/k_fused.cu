@@ -338,6 +338,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // a clip mostly stay on one SM (per-clip state changes rarely, the row shared by two
         // tiles is re-read one tile later) and the SMs still finish together.
         uint32_t slot = 0, phase = 0;
+        const uint64_t pol_stream = l2_policy_evict_first();
         const int chunks16 = p.tile_stride >> 4;
         const int CH = p.chunk;
         int i = 0;
@@ -370,7 +371,10 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         } else {
                             const uint32_t bytes = (uint32_t(d.j_cnt) + 1u) * 2048u;
                             mbar_arrive_expect_tx(&full[slot], bytes);
-                            bulk_g2s(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot]);
+                            if (p.l2_hints)
+                                bulk_g2s_hint(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot], pol_stream);
+                            else
+                                bulk_g2s(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot]);
                         }
                     }
                     if (++slot == S) { slot = 0; phase ^= 1u; }
@@ -423,6 +427,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         };
 
         uint32_t slot = 0, phase = 0;
+        const uint64_t pol_keep = l2_policy_evict_last();
+        const bool keep_l2 = kMel && p.l2_hints && p.do_minmax;   // re-read by k_logmel_post
         uint32_t zbits = 0;
         int zb_clip = -1;
         const size_t lane_off = size_t(lane) * p.T * p.C;          // out[b, m = lane + 32 r, t, c]
@@ -614,7 +620,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                                 a1 = __logf(a1 + 1e-8f);
                             }
                             if ((C & 1) == 0) {
-                                *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                                if (keep_l2) st_f2_hint(o, a0, a1, pol_keep);
+                                else *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
                             } else {
                                 o[0] = a0;
                                 if (has1) o[1] = a1;

@@ -127,6 +127,31 @@ def test_cfg3_four_channel_magphase_labels(engine, workload_factory):
     assert nmax_err(got, _oracle(w, d, mode='logmel_minmax')[0]) < TOL
 
 
+def test_wide_mel_matrix_uses_all_bins(engine, workload_factory):
+    """A mel matrix whose support reaches above bin 128 (80 bins, 125-7600 Hz) runs the
+    all-bins variant of the fused mel epilogue; the default matrix is restored afterwards."""
+    from challenge_b200 import _lib as L
+    from oracle import transforms as OT
+    w = workload_factory(2)
+    d = _draw(w, 4, 300, seed=77)
+    try:
+        engine.set_mel(80, upper_edge_hertz=7600.0)
+        engine.upload_plan(d)
+        mel_fn = OT.magphase_to_mel(80, upper_edge_hertz=7600.0)
+        for mode, name in [(L.FEAT_MEL, 'mel'), (L.FEAT_LOGMEL_MINMAX, 'logmel_minmax')]:
+            got = engine.features(mode).cpu().numpy()
+            ref = _oracle(w, d, mode=name, mel_fn=mel_fn)[0]
+            assert got.shape == ref.shape == (4, 80, 300, 2)
+            assert nmax_err(got, ref) < TOL, name
+        # a matrix with filters wider than the fused epilogue takes is refused, not mis-computed
+        engine.set_mel(40, lower_edge_hertz=80.0, upper_edge_hertz=7600.0)
+        engine.upload_plan(d)
+        with pytest.raises(NotImplementedError):
+            engine.features(L.FEAT_MEL)
+    finally:
+        engine.set_mel(80)
+
+
 def test_background_tiling_and_short_banks(engine, workload_factory):
     """Backgrounds shorter than n_frame are tiled then cropped (pipeline.py:29-35)."""
     from challenge_b200 import _lib as L
