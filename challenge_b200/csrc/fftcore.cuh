@@ -23,9 +23,66 @@
 
 namespace iris {
 
-struct cpx {
+struct alignas(8) cpx {
     float x, y;
 };
+
+// ---- complex arithmetic on packed pairs ----
+// On sm_100a a cpx lives in an aligned 64-bit register pair and every operation below is ONE
+// packed FP32 instruction (PTX add/mul/fma.f32x2 -> SASS FADD2 / FMUL2 / FFMA2: two IEEE fp32
+// results per issue slot).  The operand swaps, sign patterns and scalar broadcasts written here
+// as re-packed pairs ({a.y, -a.x}, {s, s}, ...) cost nothing: ptxas folds them into the
+// .LO_HI / .NP / .F32 operand modifiers of the packed instructions (checked with cuobjdump).
+// The host build (unit tests of the index maps and the math) uses the scalar forms.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long cx_pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ cpx cx_up(unsigned long long r) {
+    cpx a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+// (a.x + b.x, a.y + b.y)
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(cx_pk(a.x, a.y)), "l"(cx_pk(b.x, b.y)));
+    return cx_up(d);
+}
+// (a.x * b.x, a.y * b.y)
+__device__ __forceinline__ cpx cmul2(cpx a, cpx b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(cx_pk(a.x, a.y)), "l"(cx_pk(b.x, b.y)));
+    return cx_up(d);
+}
+// (a.x * b.x + c.x, a.y * b.y + c.y)
+__device__ __forceinline__ cpx cfma2(cpx a, cpx b, cpx c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(cx_pk(a.x, a.y)), "l"(cx_pk(b.x, b.y)), "l"(cx_pk(c.x, c.y)));
+    return cx_up(d);
+}
+#else
+inline cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
+inline cpx cmul2(cpx a, cpx b) { return cpx{a.x * b.x, a.y * b.y}; }
+inline cpx cfma2(cpx a, cpx b, cpx c) { return cpx{a.x * b.x + c.x, a.y * b.y + c.y}; }
+#endif
+IRIS_HD cpx csub(cpx a, cpx b) { return cadd(a, cpx{-b.x, -b.y}); }
+IRIS_HD cpx cscale(cpx a, float s) { return cmul2(a, cpx{s, s}); }
+// a + s * b
+IRIS_HD cpx caxpy(float s, cpx b, cpx a) { return cfma2(cpx{s, s}, b, a); }
+// -i * a
+IRIS_HD cpx cmuli_neg(cpx a) { return cpx{a.y, -a.x}; }
+// a * w: two packed instructions.  The swap / sign pattern sits on the ACCUMULATOR of the
+// second one so that a compile-time w becomes two 32-bit immediates (with the swap on a
+// multiplicand ptxas has to build the (w.y, w.y) pair in registers first: 2 extra MOVs).
+IRIS_HD cpx cmul(cpx a, cpx w) {
+    const cpx t = cmul2(a, cpx{w.y, w.y});              // (a.x w.y, a.y w.y)
+    return cfma2(a, cpx{w.x, w.x}, cpx{-t.y, t.x});      // (a.x w.x - a.y w.y, a.y w.x + a.x w.y)
+}
 
 // ---- compile-time trigonometry (double precision Taylor on a reduced octant) ----
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -73,17 +130,17 @@ IRIS_HD cpx mul_w(cpx a) {
     } else if constexpr (4 * n == 3 * DEN) {
         return cpx{-a.y, a.x};
     } else if constexpr (8 * n == DEN) {
-        return cpx{(a.x + a.y) * h, (a.y - a.x) * h};
+        return cscale(cadd(a, cpx{a.y, -a.x}), h);        // ((x + y) h, (y - x) h)
     } else if constexpr (8 * n == 3 * DEN) {
-        return cpx{(a.y - a.x) * h, -(a.x + a.y) * h};
+        return cscale(cadd(a, cpx{-a.y, a.x}), -h);       // ((y - x) h, -(x + y) h)
     } else if constexpr (8 * n == 5 * DEN) {
-        return cpx{-(a.x + a.y) * h, (a.x - a.y) * h};
+        return cscale(cadd(a, cpx{a.y, -a.x}), -h);       // (-(x + y) h, (x - y) h)
     } else if constexpr (8 * n == 7 * DEN) {
-        return cpx{(a.x - a.y) * h, (a.x + a.y) * h};
+        return cscale(cadd(a, cpx{-a.y, a.x}), h);        // ((x - y) h, (x + y) h)
     } else {
         constexpr float c = float(cx_cos2pi(n, DEN));
         constexpr float s = float(cx_sin2pi(n, DEN));
-        return cpx{a.x * c + a.y * s, a.y * c - a.x * s};
+        return cmul(a, cpx{c, -s});                       // (x c + y s, y c - x s)
     }
 }
 
@@ -94,22 +151,22 @@ template <>
 struct Fft<2> {
     static IRIS_HD void run(cpx (&v)[2]) {
         cpx a = v[0], b = v[1];
-        v[0] = cpx{a.x + b.x, a.y + b.y};
-        v[1] = cpx{a.x - b.x, a.y - b.y};
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
     }
 };
 
 template <>
 struct Fft<4> {
     static IRIS_HD void run(cpx (&v)[4]) {
-        cpx t0{v[0].x + v[2].x, v[0].y + v[2].y};
-        cpx t1{v[0].x - v[2].x, v[0].y - v[2].y};
-        cpx t2{v[1].x + v[3].x, v[1].y + v[3].y};
-        cpx t3{v[1].y - v[3].y, v[3].x - v[1].x};  // -i * (v1 - v3)
-        v[0] = cpx{t0.x + t2.x, t0.y + t2.y};
-        v[1] = cpx{t1.x + t3.x, t1.y + t3.y};
-        v[2] = cpx{t0.x - t2.x, t0.y - t2.y};
-        v[3] = cpx{t1.x - t3.x, t1.y - t3.y};
+        const cpx t0 = cadd(v[0], v[2]);
+        const cpx t1 = csub(v[0], v[2]);
+        const cpx t2 = cadd(v[1], v[3]);
+        const cpx t3 = cmuli_neg(csub(v[1], v[3]));  // -i * (v1 - v3)
+        v[0] = cadd(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[2] = csub(t0, t2);
+        v[3] = csub(t1, t3);
     }
 };
 
@@ -157,8 +214,6 @@ template <>
 struct Fft<32> {
     static IRIS_HD void run(cpx (&v)[32]) { fft_ct<32, 4>(v); }
 };
-
-IRIS_HD cpx cmul(cpx a, cpx w) { return cpx{a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
 
 // ---- exchange-buffer geometry (per half-warp slot, 4 rounds of 8 k1 values) ----
 // Round rho holds k1 in [8*rho, 8*rho+8) as 4 rows a (k1 pair 8*rho+2a, +1) of

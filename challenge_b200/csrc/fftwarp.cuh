@@ -57,14 +57,12 @@ IRIS_HD void warp_pass1(cpx (&v)[16], TwLoad tw) {
     }
 }
 
-// one DIF element of pass 2: u = (a + s*b) * t
-IRIS_HD cpx warp_dif(cpx a, cpx b, float s, float tx, float ty) {
-#if defined(__CUDA_ARCH__)
-    const cpx d{fmaf(s, b.x, a.x), fmaf(s, b.y, a.y)};
-#else
-    const cpx d{a.x + s * b.x, a.y + s * b.y};
-#endif
-    return cmul(d, cpx{tx, ty});
+// one DIF element of pass 2: u = (a + s*b) * (odd ? t : 1).  The odd half-warp multiplies by
+// the compile-time twiddle t under a predicate (no selects); the even half keeps the sum.
+IRIS_HD cpx warp_dif(cpx a, cpx b, float s, bool odd, float tx, float ty) {
+    cpx d = caxpy(s, b, a);
+    if (odd) d = cmul(d, cpx{tx, ty});
+    return d;
 }
 
 }  // namespace iris

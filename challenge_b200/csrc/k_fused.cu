@@ -449,7 +449,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const float2 x = src[32 * q];
-                    v[q] = cpx{g0 * x.x, g0 * x.y};
+                    v[q] = cscale(cpx{x.x, x.y}, g0);
                 }
                 __syncwarp();
                 mbar_arrive_if(&empty[slot], l0);
@@ -465,8 +465,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
                         const float2 x = src[32 * q];
-                        v[q].x = fmaf(gn, x.x, v[q].x);
-                        v[q].y = fmaf(gn, x.y, v[q].y);
+                        v[q] = caxpy(gn, cpx{x.x, x.y}, v[q]);
                     }
                 }
                 __syncwarp();
@@ -509,10 +508,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             if (do_fft) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    v[q].x *= w8[q];
-                    v[q].y *= w8[q];
-                    v[q + 8].x = fmaf(-w8[q], v[q + 8].x, v[q + 8].x);
-                    v[q + 8].y = fmaf(-w8[q], v[q + 8].y, v[q + 8].y);
+                    v[q] = cscale(v[q], w8[q]);
+                    v[q + 8] = caxpy(-w8[q], v[q + 8], v[q + 8]);
                 }
                 warp_pass1(v, [&](int q, float& a, float& bb, float& c, float& d) {
                     const float4 w = s_tw1[q * 32];
@@ -530,10 +527,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                     const float4 a = *reinterpret_cast<const float4*>(row + 16 * m);
                     const float4 c = *reinterpret_cast<const float4*>(row + 16 * (m + 8));
                     constexpr_for_pair(m, [&](float c0, float s0, float c1, float s1) {
-                        const float tx0 = par ? c0 : 1.f, ty0 = par ? s0 : 0.f;
-                        const float tx1 = par ? c1 : 1.f, ty1 = par ? s1 : 0.f;
-                        u[2 * m] = warp_dif(cpx{a.x, a.y}, cpx{c.x, c.y}, sgn, tx0, ty0);
-                        u[2 * m + 1] = warp_dif(cpx{a.z, a.w}, cpx{c.z, c.w}, sgn, tx1, ty1);
+                        u[2 * m] = warp_dif(cpx{a.x, a.y}, cpx{c.x, c.y}, sgn, par != 0, c0, s0);
+                        u[2 * m + 1] = warp_dif(cpx{a.z, a.w}, cpx{c.z, c.w}, sgn, par != 0, c1, s1);
                     });
                 }
                 Fft<16>::run(u);
@@ -559,10 +554,12 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 for (int r = 0; r < 4; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
                 if (do_fft) {   // warp-uniform
                     auto emit = [&](int f, int bit, cpx zf, cpx zm) {
-                        const float r0 = zf.x + zm.x, i0 = zf.y - zm.y;
-                        const float r1 = zf.y + zm.y, i1 = zm.x - zf.x;
-                        float m0 = sqrt_approx(fmaf(r0, r0, i0 * i0));
-                        float m1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
+                        // (re ch0, re ch1) and (im ch0, im ch1) of the split, as packed pairs
+                        const cpx re = cadd(zf, zm);
+                        const cpx im = cadd(cpx{zf.y, -zf.x}, cpx{-zm.y, zm.x});
+                        const cpx sq = cfma2(im, im, cmul2(re, re));
+                        float m0 = sqrt_approx(sq.x);
+                        float m1 = sqrt_approx(sq.y);
                         if ((zbits >> bit) & 1u) { m0 = 0.f; m1 = 0.f; }   // |x| * 0 == +0
                         const unsigned fi = unsigned(f - f_lo);
                         if (fi < unsigned(f_n)) mg[fi] = make_float2(m0, m1);
@@ -584,19 +581,17 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         const int L = p.mel_L[r];   // 0 for r >= ceil(n_mel / 32); uniform
                         if (L == 0) break;
                         const float2* a = mg + ms[32 * r];
-                        float s0 = 0.f, s1 = 0.f;
+                        cpx sacc{0.f, 0.f};   // (ch0, ch1)
 #pragma unroll
                         for (int q = 0; q < kMaxFilter; q += 2) {   // L is even (iris_set_mel pads)
                             if (q >= L) break;                        // uniform
                             const float2 x0 = a[q], x1 = a[q + 1];
                             const float w0 = wr[32 * q], w1 = wr[32 * q + 32];
-                            s0 = fmaf(w0, x0.x, s0);
-                            s1 = fmaf(w0, x0.y, s1);
-                            s0 = fmaf(w1, x1.x, s0);
-                            s1 = fmaf(w1, x1.y, s1);
+                            sacc = caxpy(w0, cpx{x0.x, x0.y}, sacc);
+                            sacc = caxpy(w1, cpx{x1.x, x1.y}, sacc);
                         }
-                        acc0[r] = s0;
-                        acc1[r] = s1;
+                        acc0[r] = sacc.x;
+                        acc1[r] = sacc.y;
                         wr += 32 * L;
                     }
                     __syncwarp();   // mags are consumed before the next frame's exchange

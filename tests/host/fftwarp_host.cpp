@@ -70,8 +70,8 @@ int main() {
             memcpy(a, &xch[xw_read_off(k1, m)], 16);
             memcpy(b, &xch[xw_read_off(k1, m + 8)], 16);
             const float* t = &ts[4 * (m * 2 + p)];
-            u[2 * m] = warp_dif(cpx{a[0], a[1]}, cpx{b[0], b[1]}, s, t[0], t[1]);
-            u[2 * m + 1] = warp_dif(cpx{a[2], a[3]}, cpx{b[2], b[3]}, s, t[2], t[3]);
+            u[2 * m] = warp_dif(cpx{a[0], a[1]}, cpx{b[0], b[1]}, s, p != 0, t[0], t[1]);
+            u[2 * m + 1] = warp_dif(cpx{a[2], a[3]}, cpx{b[2], b[3]}, s, p != 0, t[2], t[3]);
         }
         Fft<16>::run(u);
         for (int j = 0; j < 16; ++j) Y[lane][j] = u[j];
