@@ -70,9 +70,8 @@ constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 constexpr int OFF_FULL = 0;                                  // uint64 full[<= 3]
 constexpr int OFF_EMPTY = 32;                                // uint64 empty[<= 3]
 constexpr int OFF_RING = 64;
-constexpr int OFF_TW1 = OFF_RING + kRing * kTileBlockBytes;  // float4 [8][32]
-constexpr int OFF_TS = OFF_TW1 + 8 * 32 * 16;                // float4 [8][2]
-constexpr int OFF_MSTART = OFF_TS + 8 * 2 * 16;              // uint32 [kMaxMel]
+constexpr int OFF_TW1 = OFF_RING + kRing * kTileBlockBytes;  // float4 [2][32]: {w, w^2}, {w^4, w^8}, w = W512^lane
+constexpr int OFF_MSTART = OFF_TW1 + 2 * 32 * 16;            // uint32 [kMaxMel]
 constexpr int OFF_MW = OFF_MSTART + kMaxMel * 4;             // float [mel_taps][32]
 static_assert(OFF_TW1 % 16 == 0 && OFF_MW % 16 == 0, "table alignment");
 
@@ -85,7 +84,10 @@ __host__ __device__ inline uint32_t off_slots(int mel_taps, int fr) {
 __host__ __device__ inline uint32_t slot_bytes(int fr) { return uint32_t(fr + 1) * 2048u; }
 // stage buffers per CTA: the modes that write whole spectrograms trade one stage buffer for
 // the store staging area below
-__host__ __device__ constexpr int slots_of(int mode) { return (mode == FM_MEL || mode == FM_ACTIVITY) ? 3 : 2; }
+#ifndef IRIS_MEL_SLOTS
+#define IRIS_MEL_SLOTS 3
+#endif
+__host__ __device__ constexpr int slots_of(int mode) { return (mode == FM_MEL || mode == FM_ACTIVITY) ? IRIS_MEL_SLOTS : 2; }
 // staging of a tile's [257 bins][FR frames] x 16 B output pieces (16-byte columns XOR-swizzled
 // by the bin so that both the per-frame writes and the per-bin reads are conflict-free)
 __host__ __device__ inline uint32_t stage_bytes(int fr) { return uint32_t(kBins) * uint32_t(fr) * 16u; }
@@ -303,10 +305,13 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 
     // ---- one-time setup: tables, barriers, finite data in the stage buffers ----
     {
+        // base powers of the inter-pass twiddle (fftwarp.cuh): p.tw1[q][n2] = {w^(2q), w^(2q+1)}
         float4* s_tw1 = reinterpret_cast<float4*>(sm + OFF_TW1);
-        for (int i = tid; i < 8 * 32; i += blockDim.x) s_tw1[i] = p.tw1[i];
-        float4* s_ts = reinterpret_cast<float4*>(sm + OFF_TS);
-        for (int i = tid; i < 16; i += blockDim.x) s_ts[i] = p.ts[i];
+        if (tid < 32) {
+            const float4 q0 = p.tw1[tid], q1 = p.tw1[32 + tid], q2 = p.tw1[64 + tid], q4 = p.tw1[128 + tid];
+            s_tw1[tid] = make_float4(q0.z, q0.w, q1.x, q1.y);
+            s_tw1[32 + tid] = make_float4(q2.x, q2.y, q4.x, q4.y);
+        }
         if (kMel) {
             uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
             for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = i < p.n_mel ? p.mel_info[i] : 0u;
@@ -408,7 +413,6 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         for (int i = 0; i < 8; ++i) w8[i] = p.hann[lane + 32 * i];
         unsigned char* xch = sm + off_xch(p.mel_taps) + warp * kXwBytes;
         const float4* s_tw1 = reinterpret_cast<const float4*>(sm + OFF_TW1) + lane;
-        const float4* s_ts = reinterpret_cast<const float4*>(sm + OFF_TS) + par;
         const unsigned char* my_rows = slots + j * 2048 + lane * 8;
         // running per-clip extrema of this lane (flushed when the clip changes)
         float mn = __int_as_float(0x7f800000), mx = 0.f;
@@ -511,10 +515,10 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                     v[q] = cscale(v[q], w8[q]);
                     v[q + 8] = caxpy(-w8[q], v[q + 8], v[q + 8]);
                 }
-                warp_pass1(v, [&](int q, float& a, float& bb, float& c, float& d) {
-                    const float4 w = s_tw1[q * 32];
-                    a = w.x; bb = w.y; c = w.z; d = w.w;
-                });
+                {
+                    const float4 wa = s_tw1[0], wb = s_tw1[32];
+                    warp_pass1(v, cpx{wa.x, wa.y}, cpx{wa.z, wa.w}, cpx{wb.x, wb.y}, cpx{wb.z, wb.w});
+                }
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
                     *reinterpret_cast<float2*>(xch + xw_write_off(k, lane)) = make_float2(v[k].x, v[k].y);

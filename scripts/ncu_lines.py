@@ -21,7 +21,7 @@ for r in rows:
     def num(k):
         try: return int(d.get(k, '0').replace(',', ''))
         except ValueError: return 0
-    a = agg[line_key]
+    a = agg[line_key or ('?', 0)]
     a[0] += num('# Samples'); a[1] += num('Instructions Executed'); a[2] += num('L1 Wavefronts Shared Excessive')
     for k in hdr:
         if k.startswith('stall_') and 'Not Issued' not in k:
@@ -32,10 +32,10 @@ print('total samples %d, total warp-instr %d' % (tot_s, tot_i))
 print('--- top lines by stall samples')
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     st = ' '.join('%s:%d' % x for x in a[3].most_common(3))
-    print('%5.1f%% smp %5.1f%% ins  xwf %8d  %s:%s  %-70s | %s' % (100*a[0]/tot_s, 100*a[1]/tot_i, a[2], k[0], k[1], src_text.get(k, '')[:70], st))
+    print('%5.1f%% smp %5.1f%% ins  xwf %8d  %s:%s  %-70s | %s' % (100*a[0]/tot_s, 100*a[1]/tot_i, a[2], k[0], k[1], (src_text.get(k) or '')[:70], st))
 print('--- top lines by instructions')
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print('%5.1f%% ins %5.1f%% smp  %s:%s  %s' % (100*a[1]/tot_i, 100*a[0]/tot_s, k[0], k[1], src_text.get(k, '')[:90]))
+    print('%5.1f%% ins %5.1f%% smp  %s:%s  %s' % (100*a[1]/tot_i, 100*a[0]/tot_s, k[0], k[1], (src_text.get(k) or '')[:90]))
 tot = collections.Counter()
 for a in agg.values():
     tot.update(a[3])

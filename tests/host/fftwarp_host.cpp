@@ -53,10 +53,8 @@ int main() {
             v[i + 8].x = v[i + 8].x - w8[i] * v[i + 8].x;   // w[n + 256] = 1 - w[n]
             v[i + 8].y = v[i + 8].y - w8[i] * v[i + 8].y;
         }
-        warp_pass1(v, [&](int q, float& a, float& b, float& c, float& d) {
-            const float* t = &tw1[4 * (q * 32 + lane)];
-            a = t[0]; b = t[1]; c = t[2]; d = t[3];
-        });
+        auto twv = [&](int k) { const float* t = &tw1[4 * ((k >> 1) * 32 + lane) + 2 * (k & 1)]; return cpx{t[0], t[1]}; };
+        warp_pass1(v, twv(1), twv(2), twv(4), twv(8));
         for (int k1 = 0; k1 < 16; ++k1) memcpy(&xch[xw_write_off(k1, lane)], &v[k1], 8);
     }
     // pass 2 per lane
