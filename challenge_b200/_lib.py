@@ -76,6 +76,17 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'iris_op_cos_sim': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p]),
+    # evaluation-side chain (metrics.evaluate)
+    'iris_op_eval_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'iris_op_eval_merge': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'iris_op_eval_smooth': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    'iris_op_eval_events': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'iris_op_get_er': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 }
 PW_C2MP, PW_MP2C, PW_LOG_MAGPHASE, PW_LOG_ON_MEL, PW_MULTIPLY = range(5)
 MAP_MONO_CHAN, MAP_STEREO_MONO, MAP_MERGE_AUG = range(3)

@@ -211,7 +211,7 @@ int iris_ctx_destroy(iris_ctx* c) {
     }
     for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
                       &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->ts, &c->sched,
-                      &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops})
+                      &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops, &c->eval_scratch})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stage_free) cudaEventDestroy(c->stage_free);

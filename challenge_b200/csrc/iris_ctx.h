@@ -101,7 +101,7 @@ struct iris_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
     // stand-alone ops (iris_ops_abi.cu): dense mel matrix + column supports, small scratch
-    DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops;
+    DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops, eval_scratch;
     int mel_bins = 0;
     bool mel_fusable = false;
 };

@@ -69,4 +69,17 @@ cudaError_t launch_avg_pool_time(const float* y, float* out, int B, int T, int K
 cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out, int B, int T, int K,
                            cudaStream_t st);
 
+// k_eval.cu -- evaluation-side chain of metrics.evaluate (metrics.py:59-87, 109-133, 176-214)
+cudaError_t launch_eval_windows(const float* x, float* out, long long outer, long long T, long long inner,
+                                int frame_len, int step, int n_win, cudaStream_t st);
+cudaError_t launch_eval_merge(const float* preds, float* out, int n_win, int n_p, int K, int up, int step,
+                              int L, cudaStream_t st);
+cudaError_t launch_eval_smooth(const float* x, float* tmp, float* out, int L, int K, int k_avg, int k_max,
+                               float thr, cudaStream_t st);
+cudaError_t launch_eval_events(const float* y, int L, int K, int hop, int sr, int32_t* rows, int max_rows,
+                               int32_t* n_rows, cudaStream_t st);
+cudaError_t launch_get_er(const int32_t* gt, int m, const int32_t* pred, int pred_stride, int pred_time_col,
+                          const int32_t* n_pred_ptr, int n_pred_max, int32_t* order_p, int32_t* order_g,
+                          int32_t* out, cudaStream_t st);
+
 }  // namespace iris

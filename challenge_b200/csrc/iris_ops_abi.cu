@@ -223,4 +223,68 @@ int iris_op_cos_sim(iris_ctx* c, const float* y_true, const float* y_pred, float
     return IRIS_OK;
 }
 
+
+// ---- evaluation-side chain (k_eval.cu) ----
+int iris_op_eval_windows(iris_ctx* c, const float* x, float* out, int64_t outer, int64_t T, int64_t inner,
+                         int frame_len, int step, int n_win, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!x || !out || outer < 1 || T < 1 || inner < 1 || frame_len < 1 || step < 1)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_windows: bad argument");
+    if (int64_t(n_win) != (T + step - 1) / step)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_windows: n_win must be ceil(T / step) (pad_end=True)");
+    CU(launch_eval_windows(x, out, outer, T, inner, frame_len, step, n_win, static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
+int iris_op_eval_merge(iris_ctx* c, const float* preds, float* out, int n_win, int n_p, int K, int up,
+                       int step, int L, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!preds || !out || n_win < 1 || n_p < 1 || K < 1 || up < 1 || step < 1 || L < 1)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_merge: bad argument");
+    if (int64_t(L) > int64_t(n_win - 1) * step + int64_t(n_p) * up)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_merge: L exceeds the overlap-added length");
+    CU(launch_eval_merge(preds, out, n_win, n_p, K, up, step, L, static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
+int iris_op_eval_smooth(iris_ctx* c, const float* x, float* tmp, float* out, int L, int K, int k_avg,
+                        int k_max, float threshold, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!x || !tmp || !out || L < 1 || K < 1 || k_avg < 1 || k_max < 1 || tmp == x || tmp == out)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_smooth: bad argument");
+    CU(launch_eval_smooth(x, tmp, out, L, K, k_avg, k_max, threshold, static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
+int iris_op_eval_events(iris_ctx* c, const float* y, int L, int K, int hop, int sr, int32_t* rows,
+                        int max_rows, int32_t* n_rows, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!y || !rows || !n_rows || L < 1 || K < 1 || K > 8 || hop < 1 || sr < 1 || max_rows < 0)
+        return fail(IRIS_ERR_INVALID, "iris_op_eval_events: bad argument");
+    CU(launch_eval_events(y, L, K, hop, sr, rows, max_rows, n_rows, static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
+int iris_op_get_er(iris_ctx* c, const int32_t* gt, int m, const int32_t* pred, int pred_stride,
+                   int pred_time_col, const int32_t* n_pred, int n_pred_max, int32_t* out,
+                   iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!out || m < 0 || n_pred_max < 0 || (m && !gt) || (n_pred_max && !pred) || pred_stride < 2 ||
+        pred_time_col < 1 || pred_time_col >= pred_stride)
+        return fail(IRIS_ERR_INVALID, "iris_op_get_er: bad argument");
+    if (m > (1 << 20) || n_pred_max > (1 << 20))
+        return fail(IRIS_ERR_UNSUPPORTED, "iris_op_get_er: more than 2^20 events");
+    // sort orders of the two lists
+    CU(c->eval_scratch.reserve(size_t(m + n_pred_max + 2) * 4));
+    int32_t* order_p = c->eval_scratch.as<int32_t>();
+    int32_t* order_g = order_p + n_pred_max + 1;
+    CU(launch_get_er(gt, m, pred, pred_stride, pred_time_col, n_pred, n_pred_max, order_p, order_g, out,
+                     static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
 }  // extern "C"

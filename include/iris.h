@@ -208,6 +208,36 @@ int iris_op_avg_pool_time(iris_ctx* ctx, const float* d_y, float* d_out, int B, 
 int iris_op_cos_sim(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred, float* d_out,
                     int B, int T, int K, iris_stream stream);
 
+
+/* ---- evaluation-side chain of metrics.evaluate (metrics.py:40-90), SURVEY.md 8f rank 1 ---- */
+/* metrics.py:60-61: tf.signal.frame(x, frame_len, step, pad_end=True, axis=-2) + transpose
+ * (1, 0, 2, 3).  x [outer, T, inner] -> out [n_win, outer, frame_len, inner] with
+ * n_win = ceil(T / step) (checked), zeros past the end. */
+int iris_op_eval_windows(iris_ctx* ctx, const float* d_x, float* d_out, int64_t outer, int64_t T,
+                         int64_t inner, int frame_len, int step, int n_win, iris_stream stream);
+/* metrics.py:67-75: UpSampling1D(up) + overlap_and_add(preds) / overlap_and_add(ones) +
+ * [..., :L].  preds [n_win, n_p, K] -> out [L, K]; L <= (n_win - 1) * step + n_p * up. */
+int iris_op_eval_merge(iris_ctx* ctx, const float* d_preds, float* d_out, int n_win, int n_p, int K,
+                       int up, int step, int L, iris_stream stream);
+/* metrics.py:77-81: AveragePooling1D(k_avg, 1, 'same') -> MaxPooling1D(k_max, 1, 'same') ->
+ * `>= threshold` as 0/1 floats.  x, out [L, K]; d_tmp [L, K] scratch. */
+int iris_op_eval_smooth(iris_ctx* ctx, const float* d_x, float* d_tmp, float* d_out, int L, int K,
+                        int k_avg, int k_max, float threshold, iris_stream stream);
+/* Challenge_Metric.get_start_end_frame + output_to_metric (metrics.py:109-133, 196-214).
+ * y [L, K<=8].  d_rows int32 [max_rows, 4] = (class, start, end, int32(((start + end) / 2) *
+ * hop / sr)) ordered by class then time; d_n_rows int32 [1 + K] = total events (may exceed
+ * max_rows: rows beyond it are dropped), events per class. */
+int iris_op_eval_events(iris_ctx* ctx, const float* d_y, int L, int K, int hop, int sr,
+                        int32_t* d_rows, int max_rows, int32_t* d_n_rows, iris_stream stream);
+/* metrics.get_er (metrics.py:176-193).  d_gt int32 [m, 3] (class, start, end); d_pred int32 rows
+ * of pred_stride ints with the class in column 0 and the time in column pred_time_col
+ * ([n, 2] tensor: stride 2, column 1; rows of iris_op_eval_events: stride 4, column 3);
+ * n = *d_n_pred (clamped to n_pred_max) or n_pred_max if d_n_pred is NULL.
+ * d_out int32 [3] = (N = n + m, answer = 2 * matches, m); ER = (N - answer) / m. */
+int iris_op_get_er(iris_ctx* ctx, const int32_t* d_gt, int m, const int32_t* d_pred, int pred_stride,
+                   int pred_time_col, const int32_t* d_n_pred, int n_pred_max, int32_t* d_out,
+                   iris_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
