@@ -156,6 +156,46 @@ int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
     return IRIS_OK;
 }
 
+
+// Features from spectrogram banks: the mix + per-cell epilogue is one streaming kernel
+// (k_spec.cu); the mel modes continue with the stand-alone mel / min-max / log kernels.
+int spec_features(iris_ctx* c, int mode, float* d_out, cudaStream_t st) {
+    const bool mel = mode >= IRIS_FEAT_MEL;
+    if (mel && c->remap != IRIS_REMAP_NONE)
+        return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
+    if (mel && c->mel_bins != kBins) return fail(IRIS_ERR_INVALID, "the mel matrix must have 257 rows");
+    FusedParams p;
+    fill_common(c, p);
+    p.segs = c->d_segs;
+    p.seg_ptr = c->d_seg_ptr;
+    p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
+    p.B = c->B; p.T = c->T; p.C = c->C;
+    p.n_pairs = (c->C + 1) / 2;
+    p.c_out = c->c_out;
+    p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
+    p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
+    p.filter_k = c->filter_k;
+    p.remap = c->remap;
+    p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
+    if (!mel) {
+        p.out = d_out;
+        CU(launch_specmix(p, mode, st));
+        return IRIS_OK;
+    }
+    CU(c->spec_scratch.reserve(size_t(c->B) * kBins * c->T * 2 * c->C * 4));
+    p.out = c->spec_scratch.as<float>();
+    CU(launch_specmix(p, FM_MAGPHASE, st));
+    CU(launch_mel_project(p.out, c->mel_dense.as<float>(), c->mel_lo.as<int32_t>(), c->mel_len.as<int32_t>(),
+                          d_out, c->B, kBins, c->T, c->C, c->n_mel, st));
+    const size_t per_clip = size_t(c->n_mel) * c->T * c->C;
+    if (mode == IRIS_FEAT_LOGMEL_MINMAX) {
+        int rc = iris_op_minmax(c, 0, d_out, d_out, c->B, int64_t(per_clip), 1, st);
+        if (rc) return rc;
+    }
+    if (mode != IRIS_FEAT_MEL) CU(launch_logmel_post(d_out, nullptr, c->B, per_clip, 0, 1, st));
+    return IRIS_OK;
+}
+
 }  // namespace
 
 int iris_set_device(iris_ctx* c) {
@@ -211,7 +251,7 @@ int iris_ctx_destroy(iris_ctx* c) {
     }
     for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
                       &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->ts, &c->sched,
-                      &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops, &c->eval_scratch})
+                      &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops, &c->eval_scratch, &c->spec_scratch})
         d->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stage_free) cudaEventDestroy(c->stage_free);
@@ -313,6 +353,7 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Bank& b = c->banks[kind];
     b.ready = false;
+    b.spec = false;
     b.n_items = n_items;
     b.n_chan = n_chan;
     b.n_classes = n_classes;
@@ -402,6 +443,65 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
     return IRIS_OK;
 }
 
+int iris_specbank_register(iris_ctx* c, int kind, int n_items, int n_freq, int n_chan2, const float* specs,
+                           const int64_t* frame_offsets, const float* labels, int n_classes,
+                           iris_stream stream) {
+    if (!c || !specs || !frame_offsets) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(IRIS_ERR_INVALID, "bad bank kind");
+    if (n_items < 1) return fail(IRIS_ERR_INVALID, "empty bank");
+    if (n_freq != kBins) return fail(IRIS_ERR_UNSUPPORTED, "spectrogram banks must have 257 frequency bins");
+    if (n_chan2 < 2 || (n_chan2 & 1) || n_chan2 > 64)
+        return fail(IRIS_ERR_INVALID, "last axis of a complex spectrogram must be 2 * chan (re | im)");
+    if (kind == IRIS_BANK_VOICE && (!labels || n_classes < 1))
+        return fail(IRIS_ERR_INVALID, "voice bank needs labels [n_items, n_classes]");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Bank& b = c->banks[kind];
+    b.ready = false;
+    b.spec = true;
+    b.n_items = n_items;
+    b.n_chan = n_chan2 / 2;
+    b.n_classes = n_classes;
+    b.offsets.assign(frame_offsets, frame_offsets + n_items + 1);      // frames, cumulative
+    b.pad_offsets.assign(n_items + 1, 0);
+    b.n_frames.assign(n_items, 0);
+    b.max_frames = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int64_t t = frame_offsets[i + 1] - frame_offsets[i];
+        if (t < 1 || t > (1 << 24)) return fail(IRIS_ERR_INVALID, "spectrogram with no frames");
+        b.n_frames[i] = int32_t(t);
+        b.max_frames = std::max(b.max_frames, int(t));
+        b.pad_offsets[i + 1] = frame_offsets[i + 1] - frame_offsets[0];
+    }
+    const size_t floats = size_t(b.pad_offsets[n_items]) * kBins * n_chan2;
+    CU(b.padded.reserve(floats * 4));
+    CU(b.d_n_frames.reserve(size_t(n_items) * 4));
+    CU(cudaMemcpyAsync(b.padded.p, specs + size_t(frame_offsets[0]) * kBins * n_chan2, floats * 4,
+                       cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(b.d_n_frames.p, b.n_frames.data(), size_t(n_items) * 4, cudaMemcpyHostToDevice, st));
+    if (kind == IRIS_BANK_VOICE) {
+        CU(b.labels.reserve(size_t(n_items) * n_classes * 4));
+        CU(cudaMemcpyAsync(b.labels.p, labels, size_t(n_items) * n_classes * 4, cudaMemcpyHostToDevice, st));
+        const size_t act_bytes = size_t(n_items) * b.max_frames;
+        CU(b.activity.reserve(act_bytes));
+        CU(cudaMemsetAsync(b.activity.p, 0, act_bytes, st));
+        DevBuf d_off;
+        CU(d_off.reserve(size_t(n_items + 1) * 8));
+        CU(cudaMemcpyAsync(d_off.p, b.pad_offsets.data(), size_t(n_items + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(launch_spec_activity(b.padded.as<float>(), d_off.as<int64_t>(), n_items, kBins, n_chan2,
+                                b.max_frames, b.activity.as<uint8_t>(), st));
+        b.h_activity.resize(act_bytes);
+        CU(cudaMemcpyAsync(b.h_activity.data(), b.activity.p, act_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        d_off.release();
+    }
+    CU(cudaStreamSynchronize(st));
+    b.ready = true;
+    c->has_plan = false;
+    return IRIS_OK;
+}
+
 int iris_bank_info(iris_ctx* c, int kind, int32_t* n_items, int32_t* n_chan, int32_t* n_frames) {
     if (!c || kind < 0 || kind > 2) return fail(IRIS_ERR_INVALID, "bad argument");
     const Bank& b = c->banks[kind];
@@ -442,6 +542,8 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     const int C = bg.n_chan;
     if ((V > 0 && vb.n_chan != C) || (M > 0 && nb.n_chan != C))
         return fail(IRIS_ERR_INVALID, "all banks must have the same channel count");
+    if ((V > 0 && vb.spec != bg.spec) || (M > 0 && nb.spec != bg.spec))
+        return fail(IRIS_ERR_INVALID, "banks must be all waveforms or all spectrograms");
     const int n_tm = pl->time_masks ? pl->n_time_masks : 0;
     const int n_fm = pl->freq_masks ? pl->n_freq_masks : 0;
     if (n_tm < 0 || n_tm > 64) return fail(IRIS_ERR_UNSUPPORTED, "more than 64 time masks");
@@ -463,16 +565,21 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     auto push = [&](const Bank& bank, int id, int shift, int lo, int hi, float gain, int keep_idx) {
         if (lo >= hi) return;
         Seg s;
-        const int64_t plen = 256 * (int64_t(bank.n_frames[id]) + 1);
-        s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * ((bank.n_chan + 1) / 2) * 2;
-        s.pair_stride = int32_t(2 * plen);
+        if (bank.spec) {   // k_spec.cu: base = the item's [257, tI, 2C] array, pair_stride = tI
+            s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * kBins * 2 * bank.n_chan;
+            s.pair_stride = bank.n_frames[id];
+        } else {
+            const int64_t plen = 256 * (int64_t(bank.n_frames[id]) + 1);
+            s.base = bank.padded.as<float>() + size_t(bank.pad_offsets[id]) * ((bank.n_chan + 1) / 2) * 2;
+            s.pair_stride = int32_t(2 * plen);
+        }
         s.shift = shift;
         s.t_lo = lo;
         s.t_hi = hi;
         s.gain = gain;
         s.keep_idx = keep_idx;
         c->h_segs.push_back(s);
-        c->h_seg_len.push_back(bank.offsets[id + 1] - bank.offsets[id]);
+        c->h_seg_len.push_back(bank.spec ? int64_t(bank.n_frames[id]) : bank.offsets[id + 1] - bank.offsets[id]);
     };
     char msg[160];
     int max_segs = 1;
@@ -561,7 +668,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         }
         c->h_seg_ptr[b + 1] = int32_t(c->h_segs.size());
         max_segs = std::max(max_segs, c->h_seg_ptr[b + 1] - c->h_seg_ptr[b]);
-        if (c->h_seg_ptr[b + 1] - c->h_seg_ptr[b] > fused_max_segments()) {
+        if (!bg.spec && c->h_seg_ptr[b + 1] - c->h_seg_ptr[b] > fused_max_segments()) {
             snprintf(msg, sizeof msg, "clip %d mixes %d segments; the fused kernel takes at most %d", b,
                      c->h_seg_ptr[b + 1] - c->h_seg_ptr[b], fused_max_segments());
             return fail(IRIS_ERR_UNSUPPORTED, msg);
@@ -630,6 +737,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     c->remap = pl->chan_remap;
     c->c_out = c_out;
     c->max_segs = max_segs;
+    c->spec_mode = bg.spec;
     c->has_plan = true;
     c->labels_done = false;
     return IRIS_OK;
@@ -657,6 +765,7 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     }
     const bool mel = mode >= IRIS_FEAT_MEL;
     if (mel && c->n_mel == 0) return fail(IRIS_ERR_STATE, "iris_set_mel not called");
+    if (c->spec_mode) return spec_features(c, mode, d_out, st);
     if (mel && !c->mel_fusable)
         return fail(IRIS_ERR_UNSUPPORTED,
                     "a mel filter wider than 16 bins (or more than 64 taps over the 32-filter rounds): run "
@@ -779,6 +888,10 @@ int iris_plan_bytes(iris_ctx* c, int mode, const uint8_t* host_keep, int64_t* by
         if (s.keep_idx >= 0 && host_keep && !host_keep[s.keep_idx]) continue;
         // frames [t_lo, t_hi) read the samples of rows t_lo+shift .. t_hi+shift once,
         // never more than the source holds
+        if (c->spec_mode) {   // [257, frames, 2C] cells of the frames the segment covers
+            in += int64_t(s.t_hi - s.t_lo) * kBins * 2 * c->C * 4;
+            continue;
+        }
         const int64_t samples = std::min<int64_t>(int64_t(s.t_hi - s.t_lo + 1) * 256, c->h_seg_len[i]);
         in += samples * 4 * c->C;
     }

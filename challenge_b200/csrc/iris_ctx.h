@@ -53,6 +53,7 @@ struct DevBuf {
 
 struct Bank {
     bool ready = false;
+    bool spec = false;                 // items are pre-computed spectrograms [257, t, 2C] (k_spec.cu)
     int n_items = 0, n_chan = 0, n_classes = 0;
     std::vector<int64_t> offsets;      // samples per channel, cumulative
     std::vector<int64_t> pad_offsets;  // padded floats per channel, cumulative
@@ -101,7 +102,8 @@ struct iris_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
     // stand-alone ops (iris_ops_abi.cu): dense mel matrix + column supports, small scratch
-    DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops, eval_scratch;
+    DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops, eval_scratch, spec_scratch;
+    bool spec_mode = false;            // the uploaded plan mixes spectrogram banks
     int mel_bins = 0;
     bool mel_fusable = false;
 };

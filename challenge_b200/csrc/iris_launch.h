@@ -69,6 +69,11 @@ cudaError_t launch_avg_pool_time(const float* y, float* out, int B, int T, int K
 cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out, int B, int T, int K,
                            cudaStream_t st);
 
+// k_spec.cu -- spectrogram-format banks (the reference's pickled [257, t, 2C] lists)
+cudaError_t launch_spec_activity(const float* specs, const int64_t* frame_off, int n_items, int F, int W,
+                                 int max_frames, uint8_t* activity, cudaStream_t st);
+cudaError_t launch_specmix(const FusedParams& p, int mode, cudaStream_t st);
+
 // k_eval.cu -- evaluation-side chain of metrics.evaluate (metrics.py:59-87, 109-133, 176-214)
 cudaError_t launch_eval_windows(const float* x, float* out, long long outer, long long T, long long inner,
                                 int frame_len, int step, int n_win, cudaStream_t st);

@@ -90,9 +90,38 @@ class Engine:
         self.n_mel = w.shape[1]
         self.mel_matrix = w
 
+    def register_spec_bank(self, kind, specs, labels=None):
+        """``specs``: list of pre-computed complex spectrograms ``[257, t_i, 2*chan]`` -- the
+        reference's own bank format (``utils.load_data`` pickles, consumed by
+        pipeline.py:113-175).  Mixed in the spectrogram domain (k_spec.cu)."""
+        items = [np.ascontiguousarray(x, np.float32) for x in specs]
+        F, W = items[0].shape[0], items[0].shape[2]
+        assert all(x.ndim == 3 and x.shape[0] == F and x.shape[2] == W for x in items), \
+            'each spec must be a 3D-tensor [freq, time, chan*2]'
+        offsets = np.zeros(len(items) + 1, np.int64)
+        offsets[1:] = np.cumsum([x.shape[1] for x in items])
+        packed = np.concatenate([x.reshape(-1) for x in items])
+        lab, n_classes = None, 0
+        if labels is not None:
+            lab = np.ascontiguousarray(labels, np.float32)
+            assert lab.shape[0] == len(items)
+            n_classes = lab.shape[1]
+        L.check(self.lib.iris_specbank_register(
+            self._ctx, kind, len(items), F, W, packed.ctypes.data, offsets.ctypes.data,
+            lab.ctypes.data if lab is not None else None, n_classes, self._stream()))
+        frames = np.zeros(len(items), np.int32)
+        L.check(self.lib.iris_bank_info(self._ctx, kind, None, None, frames.ctypes.data))
+        self.bank_frames[kind] = frames
+        self.bank_chan = W // 2
+        if kind == L.BANK_VOICE:
+            self.n_classes = n_classes
+        return frames
+
     def register_bank(self, kind, waveforms, labels=None, normalize=True):
         """``waveforms``: list of float32 ``[C, N_i]`` arrays (the audio load_wav reads,
         data_utils.py:19).  ``labels``: ``[n_items, K]`` one-hot rows (voice bank)."""
+        if np.asarray(waveforms[0]).ndim == 3:
+            return self.register_spec_bank(kind, waveforms, labels=labels)
         waves = [np.ascontiguousarray(w, np.float32) for w in waveforms]
         n_chan = waves[0].shape[0]
         assert all(w.ndim == 2 and w.shape[0] == n_chan for w in waves), \

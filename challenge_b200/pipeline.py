@@ -2,10 +2,15 @@
 
 The reference zips three shuffled ``tf.data`` streams of PRE-COMPUTED complex spectrograms and
 maps ``merge_complex_specs`` over them, one sample at a time on one host thread
-(pipeline.py:113-175).  Here the banks are WAVEFORMS (``[chan, samples]``; the STFT of
-``data_utils.load_wav`` moved into the per-step GPU path) registered once in HBM; the host
-only draws the randomness of a whole batch in the reference's draw order
-(``plan.draw_batch``) and the fused kernel produces ``batch`` samples per launch.
+(pipeline.py:113-175).  Here the banks are registered once in HBM, in either format:
+
+* WAVEFORMS ``[chan, samples]`` -- the fast path: the STFT of ``data_utils.load_wav`` moves into
+  the per-step fused kernel (time-domain mix, one FFT per output frame);
+* the reference's own SPECTROGRAMS ``[257, time, chan*2]`` (``utils.load_data`` pickles): mixed in
+  the spectrogram domain by a streaming kernel with the reference's arithmetic (k_spec.cu).
+
+The host only draws the randomness of a whole batch in the reference's draw order
+(``plan.draw_batch``) and one launch produces ``batch`` samples.
 
 ``make_pipeline`` returns an :class:`IrisDataset` with the slice of the ``tf.data`` surface
 that ``sj_train.make_dataset`` (sj_train.py:92-130) uses -- ``map``, ``batch``, ``prefetch``,
@@ -149,9 +154,9 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
                         t_axis=1, min_ratio=2 / 3, min_noise_ratio=1 / 2, snr=-20,
                         seperate_noise_voice=False, *, draws=None):
     '''
-    pipeline.py:6-110 for ONE sample given as waveforms: ``background`` [chan, samples],
-    ``voices_and_labels`` = (list of [chan, samples] voices -- the whole padded_batch group --,
-    labels [n, n_classes]), ``noises`` = list of [chan, samples] or None.
+    pipeline.py:6-110 for ONE sample.  ``background`` [freq, time, chan2] (the reference's
+    format) or a waveform [chan, samples]; ``voices_and_labels`` = (the whole padded_batch
+    group of voices in the same format, labels [n, n_classes]); ``noises`` likewise or None.
 
     OUTPUT:
         complex_spec: (freq, time, chan2)
@@ -161,10 +166,10 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
         raise NotImplementedError("seperate_noise_voice ('se' model outputs, pipeline.py:37-38) is "
                                   'outside the hot path (SURVEY.md 8f rank 4)')
     voices, labels = voices_and_labels
-    if np.asarray(background).ndim != 2:
-        raise NotImplementedError(
-            'merge_complex_specs takes waveforms [chan, samples]; mixing pre-computed '
-            'spectrogram banks is the reference\'s offline format (SURVEY.md 8f rank 2)')
+    if np.asarray(background).ndim not in (2, 3):
+        raise ValueError('background must be a spectrogram [freq, time, chan2] or a waveform [chan, samples]')
+    if t_axis != 1:
+        raise NotImplementedError('merge_complex_specs: t_axis must be 1 (the only value the reference uses)')
     eng = get_engine()
     bf = eng.register_bank(L.BANK_BG, [background])
     vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
@@ -200,13 +205,8 @@ def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan,
                  labels: [max_voices, n_frame, n_classes]
     (pipeline.py:113-175; kwargs = merge_complex_specs' min_ratio / min_noise_ratio / snr)
     '''
-    if not _is_waveform_bank(backgrounds):
-        # the reference's check (pipeline.py:136) is for 3-D spectrograms; this build starts
-        # from the waveforms those spectrograms were made of
-        raise NotImplementedError(
-            'make_pipeline takes banks of waveforms [chan, samples]: the STFT of load_wav runs '
-            'inside the fused kernel.  Pre-computed spectrogram banks are the reference\'s offline '
-            'format (SURVEY.md 8f rank 2)')
+    # pipeline.py:136 asserts 3-D spectrograms; waveform banks [chan, samples] are accepted too
+    assert len(np.asarray(backgrounds[0]).shape) in (2, 3), 'each spec must be a 3D-tensor'
     assert len(voices) == len(labels)
     assert len(np.asarray(labels[0]).shape) == 1 and np.asarray(labels[0]).shape[0] == n_classes, \
         'labels must be in the form of [n_samples, n_classes]'

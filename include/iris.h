@@ -60,6 +60,16 @@ int iris_ctx_destroy(iris_ctx* ctx);
  * tf.signal.linear_to_mel_weight_matrix returns at transforms.py:55-56.  Stored sparse. */
 int iris_set_mel(iris_ctx* ctx, int n_mel, int n_bins, const float* dense_w);
 
+/* The reference's own bank format (utils.load_data, utils.py:88-94; consumed by
+ * pipeline.make_pipeline, pipeline.py:113-175): a list of pre-computed complex spectrograms
+ * [257, t_i, 2 * chan] ([..., :chan] = re, [..., chan:] = im), packed back to back in `specs`
+ * (host or device memory); frame_offsets [n_items + 1] = cumulative t_i.  Banks registered this
+ * way are mixed in the spectrogram domain with pipeline.merge_complex_specs' arithmetic
+ * (pipeline.py:29-106); frame activity is `max over (freq, chan2) > 0` (pipeline.py:55).  All
+ * three banks of a plan must be of the same format. */
+int iris_specbank_register(iris_ctx* ctx, int kind, int n_items, int n_freq, int n_chan2,
+                           const float* specs, const int64_t* frame_offsets, const float* labels,
+                           int n_classes, iris_stream stream);
 /* Register a bank of WAVEFORMS (replaces data_utils.load_wav, data_utils.py:9-29, for every
  * source: normalize (32-34) + reflect padding now, STFT inside iris_features).
  *   packed_wav : item i is the [n_chan, len_i] row-major block starting at float
