@@ -158,7 +158,7 @@ int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
 
 
 // Features from spectrogram banks: the mix + per-cell epilogue is one streaming kernel
-// (k_spec.cu); the mel modes continue with the stand-alone mel / min-max / log kernels.
+// (k_spec.cu), for the mel modes with the projection and the per-clip extrema fused in.
 int spec_features(iris_ctx* c, int mode, float* d_out, cudaStream_t st) {
     const bool mel = mode >= IRIS_FEAT_MEL;
     if (mel && c->remap != IRIS_REMAP_NONE)
@@ -179,15 +179,31 @@ int spec_features(iris_ctx* c, int mode, float* d_out, cudaStream_t st) {
     p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
     if (!mel) {
         p.out = d_out;
-        CU(launch_specmix(p, mode, st));
+        CU(launch_specmix(p, mode, nullptr, nullptr, nullptr, st));
         return IRIS_OK;
     }
+    const size_t per_clip = size_t(c->n_mel) * c->T * c->C;
+    if (specmix_mel_smem(c->C, c->mel_f_n) <= 200 * 1024) {
+        // fused: mix -> |.| -> mel -> per-clip extrema in one pass; k_logmel_post normalises in L2
+        p.out = d_out;
+        p.do_log = mode != IRIS_FEAT_MEL;
+        p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
+        if (p.do_minmax) {
+            CU(c->minmax.reserve(size_t(c->B) * 12));
+            CU(cudaMemsetAsync(c->minmax.p, 0, size_t(c->B) * 12, st));
+            p.minmax = c->minmax.as<uint32_t>();
+        }
+        CU(launch_specmix(p, FM_MEL, c->mel_dense.as<float>(), c->mel_lo.as<int32_t>(),
+                          c->mel_len.as<int32_t>(), st));
+        if (p.do_minmax) CU(launch_logmel_post(d_out, c->minmax.as<uint32_t>(), c->B, per_clip, 1, 1, st));
+        return IRIS_OK;
+    }
+    // many channels: magnitudes through a scratch spectrogram, then the stand-alone kernels
     CU(c->spec_scratch.reserve(size_t(c->B) * kBins * c->T * 2 * c->C * 4));
     p.out = c->spec_scratch.as<float>();
-    CU(launch_specmix(p, FM_MAGPHASE, st));
+    CU(launch_specmix(p, FM_MAGPHASE, nullptr, nullptr, nullptr, st));
     CU(launch_mel_project(p.out, c->mel_dense.as<float>(), c->mel_lo.as<int32_t>(), c->mel_len.as<int32_t>(),
                           d_out, c->B, kBins, c->T, c->C, c->n_mel, st));
-    const size_t per_clip = size_t(c->n_mel) * c->T * c->C;
     if (mode == IRIS_FEAT_LOGMEL_MINMAX) {
         int rc = iris_op_minmax(c, 0, d_out, d_out, c->B, int64_t(per_clip), 1, st);
         if (rc) return rc;
@@ -889,7 +905,9 @@ int iris_plan_bytes(iris_ctx* c, int mode, const uint8_t* host_keep, int64_t* by
         // frames [t_lo, t_hi) read the samples of rows t_lo+shift .. t_hi+shift once,
         // never more than the source holds
         if (c->spec_mode) {   // [257, frames, 2C] cells of the frames the segment covers
-            in += int64_t(s.t_hi - s.t_lo) * kBins * 2 * c->C * 4;
+            // the mel modes need only the bin rows that carry a non-zero mel weight
+            const int rows = mode >= IRIS_FEAT_MEL ? c->mel_f_n : kBins;
+            in += int64_t(s.t_hi - s.t_lo) * rows * 2 * c->C * 4;
             continue;
         }
         const int64_t samples = std::min<int64_t>(int64_t(s.t_hi - s.t_lo + 1) * 256, c->h_seg_len[i]);

@@ -72,7 +72,9 @@ cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out,
 // k_spec.cu -- spectrogram-format banks (the reference's pickled [257, t, 2C] lists)
 cudaError_t launch_spec_activity(const float* specs, const int64_t* frame_off, int n_items, int F, int W,
                                  int max_frames, uint8_t* activity, cudaStream_t st);
-cudaError_t launch_specmix(const FusedParams& p, int mode, cudaStream_t st);
+cudaError_t launch_specmix(const FusedParams& p, int mode, const float* melW, const int32_t* mel_lo,
+                           const int32_t* mel_len, cudaStream_t st);
+size_t specmix_mel_smem(int C, int f_n);
 
 // k_eval.cu -- evaluation-side chain of metrics.evaluate (metrics.py:59-87, 109-133, 176-214)
 cudaError_t launch_eval_windows(const float* x, float* out, long long outer, long long T, long long inner,
