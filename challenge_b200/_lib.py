@@ -14,6 +14,7 @@ IRIS_OK, IRIS_ERR_INVALID, IRIS_ERR_CUDA, IRIS_ERR_EMPTY_RANGE, IRIS_ERR_STATE, 
 BANK_BG, BANK_VOICE, BANK_NOISE = 0, 1, 2
 FEAT_COMPLEX, FEAT_MAGPHASE, FEAT_LOG_MAGPHASE, FEAT_MEL, FEAT_LOGMEL, FEAT_LOGMEL_MINMAX = range(6)
 REMAP_NONE, REMAP_STEREO_MONO, REMAP_MERGE_AUG = 0, 1, 2
+SELECT_ALL, SELECT_VOICES, SELECT_BG_NOISE = 0, 1, 2
 
 _i32p = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)
@@ -48,6 +49,7 @@ SIGNATURES = {
     'iris_plan_upload': (C.c_int, [C.c_void_p, C.POINTER(IrisPlan), C.c_void_p]),
     'iris_labels': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'iris_features': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'iris_features_select': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'iris_stft': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                             C.c_void_p]),
     'iris_metric_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -159,7 +159,7 @@ int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
 
 // Features from spectrogram banks: the mix + per-cell epilogue is one streaming kernel
 // (k_spec.cu), for the mel modes with the projection and the per-clip extrema fused in.
-int spec_features(iris_ctx* c, int mode, float* d_out, cudaStream_t st) {
+int spec_features(iris_ctx* c, int mode, int select, float* d_out, cudaStream_t st) {
     const bool mel = mode >= IRIS_FEAT_MEL;
     if (mel && c->remap != IRIS_REMAP_NONE)
         return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
@@ -177,6 +177,11 @@ int spec_features(iris_ctx* c, int mode, float* d_out, cudaStream_t st) {
     p.filter_k = c->filter_k;
     p.remap = c->remap;
     p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
+    if (select) {   // only_voice / only_noise: the plain mix of a subset, no masks / remap / filter
+        p.seg_select = select;
+        p.tmask = nullptr; p.fmask = nullptr; p.n_tmask = 0; p.n_fmask = 0;
+        p.filter_k = 0; p.remap = IRIS_REMAP_NONE; p.c_out = c->C;
+    }
     if (!mel) {
         p.out = d_out;
         CU(launch_specmix(p, mode, nullptr, nullptr, nullptr, st));
@@ -768,7 +773,14 @@ int iris_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep, iris
 }
 
 int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
+    return iris_features_select(c, mode, IRIS_SELECT_ALL, d_out, stream);
+}
+
+int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_stream stream) {
     if (!c || !d_out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (select < IRIS_SELECT_ALL || select > IRIS_SELECT_BG_NOISE) return fail(IRIS_ERR_INVALID, "bad segment selection");
+    if (select != IRIS_SELECT_ALL && mode != IRIS_FEAT_COMPLEX)
+        return fail(IRIS_ERR_INVALID, "only_voice / only_noise are complex spectrograms (pipeline.py:37-38)");
     if (!c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
     if (mode < IRIS_FEAT_COMPLEX || mode > IRIS_FEAT_LOGMEL_MINMAX)
         return fail(IRIS_ERR_INVALID, "bad feature mode");
@@ -781,7 +793,7 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     }
     const bool mel = mode >= IRIS_FEAT_MEL;
     if (mel && c->n_mel == 0) return fail(IRIS_ERR_STATE, "iris_set_mel not called");
-    if (c->spec_mode) return spec_features(c, mode, d_out, st);
+    if (c->spec_mode) return spec_features(c, mode, select, d_out, st);
     if (mel && !c->mel_fusable)
         return fail(IRIS_ERR_UNSUPPORTED,
                     "a mel filter wider than 16 bins (or more than 64 taps over the 32-filter rounds): run "
@@ -802,6 +814,12 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
     p.remap = c->remap;
     p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
     p.out = d_out;
+    if (select) {   // only_voice / only_noise: the plain mix of a subset, no masks / remap / filter
+        p.seg_select = select;
+        p.tmask = nullptr; p.fmask = nullptr; p.n_tmask = 0; p.n_fmask = 0;
+        p.filter_k = 0; p.remap = IRIS_REMAP_NONE; p.c_out = c->C;
+        set_geometry(c, p, c->C, false);
+    }
     if (mel) {
         p.do_log = mode != IRIS_FEAT_MEL;
         p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;

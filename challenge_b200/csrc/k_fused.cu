@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
         const Seg sg = p.segs[s];
         const int lo = max(sg.t_lo, t0), hi = min(sg.t_hi, t_end);
         if (lo >= hi || (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0)) continue;
+        if ((p.seg_select == 1 && sg.keep_idx < 0) || (p.seg_select == 2 && sg.keep_idx >= 0)) continue;
         if (n < p.max_segs) {
             StageDesc e;
             e.src = sg.base + size_t(pair) * size_t(sg.pair_stride) + size_t(lo + sg.shift) * 512;

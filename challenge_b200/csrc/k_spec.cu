@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32) k_specmix(const __grid_consta
             if (s < g1) {
                 sg = p.segs[s];
                 use = sg.t_lo < t0 + kSpecTile && sg.t_hi > t0 &&
-                      !(sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0);
+                      !(sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0) &&
+                      !((p.seg_select == 1 && sg.keep_idx < 0) || (p.seg_select == 2 && sg.keep_idx >= 0));
             }
             const unsigned bal = __ballot_sync(0xffffffffu, use);
             const int pos = n + __popc(bal & ((1u << lane) - 1u));
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32) k_specmix(const __grid_consta
                     else {
                         sg = p.segs[g0 + s];
                         if (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0) continue;
+                        if ((p.seg_select == 1 && sg.keep_idx < 0) || (p.seg_select == 2 && sg.keep_idx >= 0)) continue;
                     }
                     if (t < sg.t_lo || t >= sg.t_hi) continue;
                     const size_t row = size_t(sg.pair_stride) * W;

@@ -211,13 +211,16 @@ class Engine:
             return (pl['B'], self.n_mel, pl['T'], self.bank_chan)
         return (pl['B'], 257, pl['T'], 2 * pl['c_out'])
 
-    def features(self, mode, out=None):
-        shape = self.feature_shape(mode)
+    def features(self, mode, out=None, select=L.SELECT_ALL):
+        """``select``: SELECT_VOICES / SELECT_BG_NOISE give ``only_voice`` / ``only_noise`` of
+        ``merge_complex_specs(seperate_noise_voice=True)`` (plain complex spectrograms)."""
+        pl = self._plan
+        shape = self.feature_shape(mode) if select == L.SELECT_ALL else (pl['B'], 257, pl['T'], 2 * self.bank_chan)
         if out is None:
             out = self._empty(shape)
         else:
             assert tuple(out.shape) == shape and out.is_contiguous() and out.is_cuda
-        L.check(self.lib.iris_features(self._ctx, int(mode), self._ptr(out), self._stream()))
+        L.check(self.lib.iris_features_select(self._ctx, int(mode), int(select), self._ptr(out), self._stream()))
         return out
 
     def plan_bytes(self, mode, keep=None):

@@ -137,15 +137,44 @@ class IrisDataset:
             frame, vtk, _ = eng.labels(want_vtk=not fused['frame_labels'], want_keep=False)
             x = eng.features(fused['mode'])
             y = frame if fused['frame_labels'] else vtk
-            if self._batch is None:
-                x, y = x[0], y[0]
-            batched = self._batch is not None
+            if src.get('separate'):   # (label, only_voice, only_noise), pipeline.py:107-108
+                y = (y, eng.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES),
+                     eng.features(L.FEAT_COMPLEX, select=L.SELECT_BG_NOISE))
+            # stages the fused launch did not absorb: the ones mapped BEFORE .batch() see single
+            # elements in the reference, so they run per element here (then the batch is re-stacked)
+            pre = []
+            post = []
+            # a .batch() that the lowering absorbed leaves only post-batch stages in `rest`
+            seen_batch = not any(isinstance(st, tuple) and st[0] == 'batch' for st in rest)
             for st in rest:
                 if isinstance(st, tuple) and st[0] == 'batch':
-                    batched = True          # elements were produced batched already
+                    seen_batch = True
                     continue
+                (post if seen_batch and self._batch is not None else pre).append(st)
+
+            def _el(t, i):
+                return tuple(u[i] for u in t) if isinstance(t, tuple) else t[i]
+
+            def _stack(items):
+                import torch
+                if isinstance(items[0], tuple):
+                    return tuple(torch.stack([it[k] for it in items]) for k in range(len(items[0])))
+                return torch.stack(list(items))
+            if pre:
+                xs, ys = [], []
+                for i in range(B):
+                    xi, yi = _el(x, i), _el(y, i)
+                    for st in pre:
+                        res = st(xi, yi)
+                        xi, yi = res if isinstance(res, tuple) and len(res) == 2 else (res, yi)
+                    xs.append(xi)
+                    ys.append(yi)
+                x, y = _stack(xs), _stack(ys)
+            if self._batch is None:
+                x, y = _el(x, 0), _el(y, 0)
+            for st in post:
                 res = st(x, y)
-                x, y = res if isinstance(res, tuple) else (res, y)
+                x, y = res if isinstance(res, tuple) and len(res) == 2 else (res, y)
             n += 1
             yield x, y
 
@@ -162,9 +191,6 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
         complex_spec: (freq, time, chan2)
         labels: (n_voices, time, n_classes)
     '''
-    if seperate_noise_voice:
-        raise NotImplementedError("seperate_noise_voice ('se' model outputs, pipeline.py:37-38) is "
-                                  'outside the hot path (SURVEY.md 8f rank 4)')
     voices, labels = voices_and_labels
     if np.asarray(background).ndim not in (2, 3):
         raise ValueError('background must be a spectrogram [freq, time, chan2] or a waveform [chan, samples]')
@@ -184,6 +210,10 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
     eng.upload_plan(draws)
     _, vtk, _ = eng.labels(want_vtk=True, want_keep=False)
     spec = eng.features(L.FEAT_COMPLEX)
+    if seperate_noise_voice:     # pipeline.py:37-38, 82-83, 104-108
+        only_voice = eng.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES)
+        only_noise = eng.features(L.FEAT_COMPLEX, select=L.SELECT_BG_NOISE)
+        return spec[0], (vtk[0], only_voice[0], only_noise[0])
     return spec[0], vtk[0]
 
 
@@ -210,8 +240,6 @@ def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan,
     assert len(voices) == len(labels)
     assert len(np.asarray(labels[0]).shape) == 1 and np.asarray(labels[0]).shape[0] == n_classes, \
         'labels must be in the form of [n_samples, n_classes]'
-    if kwargs.get('seperate_noise_voice'):
-        raise NotImplementedError("seperate_noise_voice is outside the hot path (SURVEY.md 8f rank 4)")
     eng = get_engine()
     bf = eng.register_bank(L.BANK_BG, list(backgrounds))
     vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
@@ -223,5 +251,6 @@ def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan,
     source = dict(engine=eng, n_frame=int(n_frame), bg_frames=bf, voice_frames=vf, noise_frames=nf,
                   max_voices=int(max_voices), max_noises=int(max_noises) if noises is not None else 0,
                   snr=kwargs.get('snr', -20), min_ratio=kwargs.get('min_ratio', 2 / 3),
-                  min_noise_ratio=kwargs.get('min_noise_ratio', 1 / 2), streams=streams)
+                  min_noise_ratio=kwargs.get('min_noise_ratio', 1 / 2), streams=streams,
+                  separate=bool(kwargs.get('seperate_noise_voice', False)))
     return IrisDataset(source)

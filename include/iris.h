@@ -131,6 +131,15 @@ int iris_labels(iris_ctx* ctx, float* d_labels_vtk, float* d_frame_labels, uint8
 /* The fused feature kernel for the uploaded plan; d_out sized per the mode's layout. */
 int iris_features(iris_ctx* ctx, int mode, float* d_out, iris_stream stream);
 
+/* merge_complex_specs(seperate_noise_voice=True) (pipeline.py:37-38, 82-83, 104-108): the same
+ * mix restricted to a subset of the sources, as a plain complex spectrogram [B,257,T,2C] (no
+ * masks, remap or filter: these are labels of the 'se' model, sj_train.py:99-105).
+ *   IRIS_SELECT_VOICES   only_voice = sum of the accepted voices
+ *   IRIS_SELECT_BG_NOISE only_noise = background + noises
+ * IRIS_SELECT_ALL is iris_features(). */
+enum { IRIS_SELECT_ALL = 0, IRIS_SELECT_VOICES = 1, IRIS_SELECT_BG_NOISE = 2 };
+int iris_features_select(iris_ctx* ctx, int mode, int select, float* d_out, iris_stream stream);
+
 /* data_utils.load_wav on one in-memory waveform (data_utils.py:9-29 minus decode/resample):
  * wav [n_chan, n_samples] (host or device) -> d_out [257, 1 + n_samples/256, 2*n_chan]. */
 int iris_stft(iris_ctx* ctx, const float* wav, int n_chan, int64_t n_samples, int normalize,

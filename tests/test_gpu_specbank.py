@@ -231,3 +231,55 @@ def test_specbank_agrees_with_waveform_path(engine):
     assert np.array_equal(_np(frame_s), frame_w) and np.array_equal(_np(keep_s), keep_w)
     for m, tol in ((L.FEAT_COMPLEX, 2e-6), (L.FEAT_LOGMEL_MINMAX, 1e-4)):
         assert nmax_err(_np(engine.features(m)), out_w[m]) <= tol
+
+
+@pytest.mark.parametrize('fmt', ['spec', 'wave'])
+def test_seperate_noise_voice(engine, mods, fmt):
+    """merge_complex_specs(seperate_noise_voice=True) (pipeline.py:37-38, 82-83, 104-108): the
+    label becomes (label, only_voice, only_noise), in both bank formats; and the 'se' chain of
+    sj_train.make_dataset (sj_train.py:99-105) on top of it."""
+    from challenge_b200 import _lib as L
+    from challenge_b200.plan import draw_batch
+    from challenge_b200.synth import synthetic_banks
+    from oracle import chain, pipeline as OP
+    P, _, DU, _ = mods
+    if fmt == 'spec':
+        bgs, voices, labels, noises = _spec_banks(55)
+        o_b, o_v, o_n = bgs, voices, noises
+    else:
+        bgs, voices, labels, noises = synthetic_banks(6, 2, n_bg=3, n_voice=8, n_noise=4, bg_seconds=3.0)
+        o_b, o_v, o_n = chain.OracleBank(bgs), chain.OracleBank(voices), chain.OracleBank(noises)
+    bf = engine.register_bank(L.BANK_BG, bgs)
+    vf = engine.register_bank(L.BANK_VOICE, voices, labels=labels)
+    nf = engine.register_bank(L.BANK_NOISE, noises)
+    d = draw_batch(np.random.default_rng(13), 5, 90, bf, vf, nf, max_voices=4, max_noises=3)
+    engine.upload_plan(d)
+    engine.labels()
+    spec = _np(engine.features(L.FEAT_COMPLEX))
+    only_voice = _np(engine.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES))
+    only_noise = _np(engine.features(L.FEAT_COMPLEX, select=L.SELECT_BG_NOISE))
+    for b in range(5):
+        ref_spec, (ref_l, ref_v, ref_n) = chain.synth_clip(o_b, o_v, labels, o_n, d, b, seperate_noise_voice=True)
+        if fmt == 'spec':
+            assert np.array_equal(spec[b], ref_spec)
+            assert np.array_equal(only_voice[b], ref_v)
+            assert np.array_equal(only_noise[b], ref_n)
+        else:
+            assert nmax_err(spec[b], ref_spec) <= 1e-5
+            assert np.abs(only_voice[b] - ref_v).max() <= 1e-5 * np.abs(ref_spec).max()
+            assert nmax_err(only_noise[b], ref_n) <= 1e-5
+    # the dataset form, through the 'se' chain: speech_enhancement_preprocess -> batch -> label_downsample(32)
+    ds = P.make_pipeline(bgs, voices, labels, noises, n_frame=64, max_voices=4, max_noises=3,
+                         seperate_noise_voice=True)
+    ds = ds.map(DU.speech_enhancement_preprocess).batch(3).map(DU.label_downsample(32))
+    n = 0
+    for x, y in ds.take(2):
+        C = 2
+        assert tuple(x.shape) == (3, 256, 64, C)
+        assert isinstance(y, tuple) and len(y) == 3
+        assert tuple(y[0].shape) == (3, 2, 3)                 # ceil(64 / 32) pooled frame labels
+        # reference quirk kept (data_utils.py:147): y[1], y[2] are cut to x.shape[-1] // 2 AFTER x was
+        # halved, i.e. to chan // 2 channels
+        assert tuple(y[1].shape) == (3, 256, 64, C // 2) and tuple(y[2].shape) == (3, 256, 64, C // 2)
+        n += 1
+    assert n == 2
