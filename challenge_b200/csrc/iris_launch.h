@@ -69,6 +69,9 @@ cudaError_t launch_avg_pool_time(const float* y, float* out, int B, int T, int K
 cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out, int B, int T, int K,
                            cudaStream_t st);
 
+cudaError_t launch_sum_pool2(const float* y, float* out, int B, int T, int K, float scale, cudaStream_t st);
+cudaError_t launch_density_labels(const float* y, float* out, size_t outer, int V, int TK, cudaStream_t st);
+
 // k_spec.cu -- spectrogram-format banks (the reference's pickled [257, t, 2C] lists)
 cudaError_t launch_spec_activity(const float* specs, const int64_t* frame_off, int n_items, int F, int W,
                                  int max_frames, uint8_t* activity, cudaStream_t st);

@@ -287,4 +287,26 @@ int iris_op_get_er(iris_ctx* c, const int32_t* gt, int m, const int32_t* pred, i
                      static_cast<cudaStream_t>(stream)));
     return IRIS_OK;
 }
+
+// ---- trainer.py label variants ----
+int iris_op_sum_pool2(iris_ctx* c, const float* y, float* out, int B, int T, int K, float scale,
+                      iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!y || !out || y == out || B < 0 || T < 1 || K < 1)
+        return fail(IRIS_ERR_INVALID, "iris_op_sum_pool2: bad argument");
+    CU(launch_sum_pool2(y, out, B, T, K, scale, static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
+int iris_op_density_labels(iris_ctx* c, const float* y, float* out, int64_t outer, int V, int64_t inner,
+                           iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!y || !out || y == out || outer < 0 || V < 1 || inner < 1 || inner > 0x7fffffff)
+        return fail(IRIS_ERR_INVALID, "iris_op_density_labels: bad argument");
+    if (V > 64) return fail(IRIS_ERR_UNSUPPORTED, "iris_op_density_labels: more than 64 voices");
+    CU(launch_density_labels(y, out, size_t(outer), V, int(inner), static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
 }  // extern "C"

@@ -266,6 +266,56 @@ __global__ void __launch_bounds__(kOpThreads) k_cos_sim(const float* __restrict_
 }
 
 // ---- launchers ----
+// trainer.preprocess_labels (trainer.py:86-94), one of its five stages:
+// avg_pool1d(y, 2, strides=2, 'SAME') * 2 on [B, T, K] -> [B, ceil(T/2), K].  SAME pads on the
+// right only (total pad <= 1) and TF averages over the valid cells, so a full pair gives
+// (a + b) / 2 * 2 = a + b (the halving and doubling are exact) and a lone last cell a / 1 * 2.
+// `scale` multiplies the result (the final `y *= multiplier`, 1 for the inner stages).
+__global__ void __launch_bounds__(kOpThreads) k_sum_pool2(const float* __restrict__ y, float* __restrict__ out,
+                                                          int B, int T, int K, float scale) {
+    const int out_len = (T + 1) / 2;
+    const size_t n = size_t(B) * out_len * K;
+    for (size_t i = blockIdx.x * size_t(kOpThreads) + threadIdx.x; i < n;
+         i += size_t(gridDim.x) * kOpThreads) {
+        const int k = int(i % K);
+        const int w = int((i / K) % out_len);
+        const size_t b = i / (size_t(K) * out_len);
+        const float a = y[(b * T + 2 * w) * K + k];
+        float v;
+        if (2 * w + 1 < T) v = __fmul_rn(__fmul_rn(__fadd_rn(a, y[(b * T + 2 * w + 1) * K + k]), 0.5f), 2.f);
+        else v = __fmul_rn(a, 2.f);
+        out[i] = scale == 1.f ? v : __fmul_rn(v, scale);
+    }
+}
+
+// trainer.to_density_labels (trainer.py:97-104): y [outer, V, T, K] -> [outer, T, K]:
+// every voice divided by max(its total over (T, K), 1e-8), then summed over the voices in
+// ascending order.  One CTA per `outer`; the totals are reduced in a fixed tree (labels are
+// 0/1, so any order gives the same integer).
+__global__ void __launch_bounds__(256) k_density_labels(const float* __restrict__ y, float* __restrict__ out,
+                                                        int V, int TK) {
+    __shared__ float red[256];
+    __shared__ float den[64];
+    const float* yo = y + size_t(blockIdx.x) * V * TK;
+    for (int v = 0; v < V; ++v) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < TK; i += 256) s += yo[size_t(v) * TK + i];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) den[v] = fmaxf(red[0], 1e-8f);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < TK; i += 256) {
+        float acc = 0.f;
+        for (int v = 0; v < V; ++v) acc = __fadd_rn(acc, __fdiv_rn(yo[size_t(v) * TK + i], den[v]));
+        out[size_t(blockIdx.x) * TK + i] = acc;
+    }
+}
+
 cudaError_t launch_axis_scale(const float* x, const float* m, float* out, size_t outer, size_t n_axis,
                               size_t inner, cudaStream_t st) {
     const size_t total = outer * n_axis * inner;
@@ -341,6 +391,19 @@ cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out,
     if (B <= 0) return cudaSuccess;
     if (K > 8) return cudaErrorInvalidValue;
     k_cos_sim<<<(B * 32 + kOpThreads - 1) / kOpThreads, kOpThreads, 0, st>>>(y_true, y_pred, out, B, T, K);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_pool2(const float* y, float* out, int B, int T, int K, float scale, cudaStream_t st) {
+    const size_t n = size_t(B) * ((T + 1) / 2) * K;
+    if (n == 0) return cudaSuccess;
+    k_sum_pool2<<<op_grid(n), kOpThreads, 0, st>>>(y, out, B, T, K, scale);
+    return cudaGetLastError();
+}
+cudaError_t launch_density_labels(const float* y, float* out, size_t outer, int V, int TK, cudaStream_t st) {
+    if (outer == 0 || TK == 0) return cudaSuccess;
+    if (V > 64 || outer > 0x7fffffff) return cudaErrorInvalidValue;
+    k_density_labels<<<unsigned(outer), 256, 0, st>>>(y, out, V, TK);
     return cudaGetLastError();
 }
 

@@ -68,11 +68,11 @@ class IrisDataset:
     # ---- lowering ----
     def _lower(self):
         """Split the stage list into what the fused kernel absorbs and the remainder."""
-        fused = dict(frame_labels=False, augment=False, remap=L.REMAP_NONE, n_out=0, filt=0,
+        fused = dict(frame_labels=False, density_labels=False, augment=False, remap=L.REMAP_NONE, n_out=0, filt=0,
                      mode=L.FEAT_COMPLEX, n_mels=0, mel_matrix=None)
         rest = []
         state = 'pre'       # pre-batch element stages -> post-batch feature stages
-        order = {'to_frame_labels': 0, 'augment': 1, 'stereo_mono': 2, 'merge_aug': 2,
+        order = {'to_frame_labels': 0, 'density_labels': 0, 'augment': 1, 'stereo_mono': 2, 'merge_aug': 2,
                  'stft_filter': 3}
         last = -1
         stages = list(self._stages)
@@ -86,6 +86,8 @@ class IrisDataset:
                 last = order[tag[0]]
                 if tag[0] == 'to_frame_labels':
                     fused['frame_labels'] = True
+                elif tag[0] == 'density_labels':            # trainer.to_density_labels (labels only)
+                    fused['density_labels'] = True
                 elif tag[0] == 'augment':
                     fused['augment'] = True
                 elif tag[0] == 'stereo_mono':
@@ -105,6 +107,8 @@ class IrisDataset:
                     and i + 1 < len(stages) and getattr(stages[i + 1], '_iris_stage', (None,))[0] == 'log_on_mel':
                 fused['mode'] = L.FEAT_LOGMEL_MINMAX
                 i += 1
+            elif state == 'post' and tag and tag[0] == 'minmax_log' and fused['mode'] == L.FEAT_MEL:
+                fused['mode'] = L.FEAT_LOGMEL_MINMAX          # trainer.minmax_log_on_mel
             elif state == 'post' and tag and tag[0] == 'log_on_mel' and fused['mode'] == L.FEAT_MEL:
                 fused['mode'] = L.FEAT_LOGMEL
             else:
@@ -137,6 +141,9 @@ class IrisDataset:
             frame, vtk, _ = eng.labels(want_vtk=not fused['frame_labels'], want_keep=False)
             x = eng.features(fused['mode'])
             y = frame if fused['frame_labels'] else vtk
+            if fused['density_labels']:
+                from .trainer import to_density_labels
+                _, y = to_density_labels(None, vtk)
             if src.get('separate'):   # (label, only_voice, only_noise), pipeline.py:107-108
                 y = (y, eng.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES),
                      eng.features(L.FEAT_COMPLEX, select=L.SELECT_BG_NOISE))

@@ -228,6 +228,17 @@ int iris_op_cos_sim(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred,
                     int B, int T, int K, iris_stream stream);
 
 
+/* ---- trainer.py label variants (trainer.py:86-104), SURVEY.md 8f rank 4 ---- */
+/* One stage of trainer.preprocess_labels: avg_pool1d(y, 2, 2, 'SAME') * 2 (* scale) on
+ * y [B, T, K] -> out [B, ceil(T/2), K]; a lone last cell is doubled (TF averages over the
+ * valid cells). */
+int iris_op_sum_pool2(iris_ctx* ctx, const float* d_y, float* d_out, int B, int T, int K, float scale,
+                      iris_stream stream);
+/* trainer.to_density_labels: y [outer, V, inner = T*K] -> out [outer, inner]: every voice
+ * divided by max(its total, 1e-8) (utils.safe_div), summed over the voices. */
+int iris_op_density_labels(iris_ctx* ctx, const float* d_y, float* d_out, int64_t outer, int V,
+                           int64_t inner, iris_stream stream);
+
 /* ---- evaluation-side chain of metrics.evaluate (metrics.py:40-90), SURVEY.md 8f rank 1 ---- */
 /* metrics.py:60-61: tf.signal.frame(x, frame_len, step, pad_end=True, axis=-2) + transpose
  * (1, 0, 2, 3).  x [outer, T, inner] -> out [n_win, outer, frame_len, inner] with

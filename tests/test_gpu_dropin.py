@@ -280,3 +280,59 @@ def test_make_pipeline_and_dataset_chain(mods):
     assert _np(xa).shape == (5, 80, 40, 2) and _np(ya).shape == (5, 40, 3)
     assert np.array_equal(_np(ya), _np(yb))
     assert nmax_err(_np(xa), _np(xb)) < 1e-4
+
+
+# ---- trainer.py label variants + the legacy trainer's dataset chain ----
+def test_trainer_label_variants(mods):
+    from challenge_b200 import trainer as TRN
+    from oracle import trainer as OT
+    rng = np.random.default_rng(3)
+    for T in (626, 300, 33, 1):
+        y = (rng.random((4, T, 3)) < 0.3).astype(np.float32) * rng.integers(1, 4, (4, T, 3)).astype(np.float32)
+        _, got = TRN.preprocess_labels(0.25)(None, y)
+        _, ref = OT.preprocess_labels(0.25)(None, y)
+        assert _np(got).shape == ref.shape and np.array_equal(_np(got), ref)
+    lab = np.zeros((5, 7, 200, 3), np.float32)
+    for b in range(5):
+        for v in range(int(rng.integers(1, 7))):
+            lo = int(rng.integers(0, 150))
+            lab[b, v, lo:lo + int(rng.integers(1, 50)), int(rng.integers(0, 3))] = 1
+    _, got = TRN.to_density_labels(None, lab)
+    _, ref = OT.to_density_labels(None, lab)
+    assert np.array_equal(_np(got), ref)
+    assert np.allclose(_np(got).sum(axis=(1, 2)), (lab.sum(axis=(2, 3)) > 0).sum(axis=1))   # each voice integrates to 1
+    _, got1 = TRN.to_density_labels(None, lab[0])                # unbatched element, as in the dataset map
+    assert np.array_equal(_np(got1), ref[0])
+    mel = rng.random((3, 80, 50, 2)).astype(np.float32)
+    assert nmax_err(_np(TRN.minmax_log_on_mel(mel)), OT.minmax_log_on_mel(mel)) <= 1e-6
+
+
+def test_trainer_make_dataset_on_pickled_banks(mods, tmp_path):
+    """trainer.make_dataset (trainer.py:107-141) on banks written in the reference's file format
+    (utils.load_data: pickled spectrogram lists, .npy integer labels with the `// 10` folding)."""
+    import types
+    from challenge_b200 import trainer as TRN, utils as U
+    rng = np.random.default_rng(4)
+    spec = lambda t: rng.standard_normal((257, t, 4)).astype(np.float32)
+    U.save_bank(str(tmp_path / 'bg.pickle'), [spec(int(rng.integers(40, 90))) for _ in range(4)])
+    U.save_bank(str(tmp_path / 'voice.pickle'), [spec(int(rng.integers(5, 30))) for _ in range(9)])
+    U.save_bank(str(tmp_path / 'noise.pickle'), [spec(int(rng.integers(5, 30))) for _ in range(5)])
+    np.save(str(tmp_path / 'labels.npy'), rng.integers(0, 3, 9) * 10 + rng.integers(0, 10, 9))
+    assert len(U.load_data(str(tmp_path / 'bg.pickle'))) == 4
+    with pytest.raises(ValueError):
+        U.load_data(str(tmp_path / 'bank.txt'))
+    cfg = types.SimpleNamespace(datapath=str(tmp_path), background_sounds='bg.pickle', voices='voice.pickle',
+                                labels='labels.npy', noises='noise.pickle', n_classes=3, n_frame=64,
+                                max_voices=4, max_noises=3, snr=-20, batch_size=3, n_mels=80, multiplier=10)
+    ds = TRN.make_dataset(cfg, training=True)
+    fused, rest = ds._lower()
+    from challenge_b200 import _lib as L
+    assert fused['mode'] == L.FEAT_LOGMEL_MINMAX and fused['augment']
+    n = 0
+    for x, y in ds.take(2):
+        assert tuple(x.shape) == (3, 80, 64, 2) and tuple(y.shape) == (3, 2, 3)
+        xs = _np(x)
+        assert np.isfinite(xs).all() and xs.max() <= 1e-6 and xs.min() >= np.log(1e-8) - 1e-3
+        assert np.all(_np(y) >= 0)
+        n += 1
+    assert n == 2
