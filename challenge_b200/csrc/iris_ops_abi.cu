@@ -309,4 +309,32 @@ int iris_op_density_labels(iris_ctx* c, const float* y, float* out, int64_t oute
     CU(launch_density_labels(y, out, size_t(outer), V, int(inner), static_cast<cudaStream_t>(stream)));
     return IRIS_OK;
 }
+
+// transforms.phase_vocoder (transforms.py:137-195)
+int iris_op_phase_vocoder(iris_ctx* c, const float* x, float* out, int n_freq, int T, int n_chan, int T_out,
+                          const int32_t* idx0, const int32_t* idx1, const float* alpha, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!x || !out || x == out || n_freq < 2 || T < 1 || n_chan < 1 || T_out < 1 || !idx0 || !idx1 || !alpha)
+        return fail(IRIS_ERR_INVALID, "iris_op_phase_vocoder: bad argument");
+    if (size_t(T_out) * 12 > 64 * 1024) return fail(IRIS_ERR_UNSUPPORTED, "iris_op_phase_vocoder: more than 5461 output frames");
+    for (int j = 0; j < T_out; ++j)
+        if (idx0[j] < 0 || idx1[j] < 0 || idx0[j] > T + 1 || idx1[j] > T + 1)
+            return fail(IRIS_ERR_INVALID, "iris_op_phase_vocoder: frame index outside the padded spectrogram");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<int32_t> blob(size_t(T_out) * 3);
+    memcpy(blob.data(), idx0, size_t(T_out) * 4);
+    memcpy(blob.data() + T_out, idx1, size_t(T_out) * 4);
+    memcpy(blob.data() + 2 * size_t(T_out), alpha, size_t(T_out) * 4);
+    void* d;
+    rc = upload_small(c, blob.data(), blob.size() * 4, st, &d);
+    if (rc) return rc;
+    const int32_t* di = static_cast<const int32_t*>(d);
+    // phase_advance = tf.linspace(0, pi * hop, n_freq) with hop = n_freq - 1, in float32
+    const float stop = float(M_PI) * float(n_freq - 1);
+    const float step = stop / float(n_freq - 1);
+    CU(launch_phase_vocoder(x, out, n_freq, T, n_chan, T_out, di, di + T_out,
+                            reinterpret_cast<const float*>(di + 2 * size_t(T_out)), step, st));
+    return IRIS_OK;
+}
 }  // extern "C"

@@ -316,6 +316,46 @@ __global__ void __launch_bounds__(256) k_density_labels(const float* __restrict_
     }
 }
 
+// transforms.phase_vocoder (transforms.py:137-195): time-stretch of a complex spectrogram
+// x [F, T, 2C] -> out [F, T_out, 2C].  Output step j interpolates the magnitudes of frames
+// i0[j], i1[j] (a zero frame past the end) with weight alpha[j] and advances the phase by the
+// wrapped phase difference of the two frames; the phase is a running sum over the steps
+// (tf.cumsum), so one thread walks one (bin, channel) row.  i0 / i1 / alpha are the host's
+// tf.range(0, T, rate) arithmetic.
+__global__ void __launch_bounds__(128) k_phase_vocoder(const float* __restrict__ x, float* __restrict__ out,
+                                                       int F, int T, int C, int T_out,
+                                                       const int32_t* __restrict__ i0,
+                                                       const int32_t* __restrict__ i1,
+                                                       const float* __restrict__ alpha, float adv_step) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= F * C) return;
+    const int f = row / C, c = row - f * C;
+    const float* xf = x + size_t(f) * T * 2 * C;
+    float* of = out + size_t(f) * T_out * 2 * C;
+    const float adv = __fmul_rn(adv_step, float(f));          // tf.linspace: start + step * i
+    const float two_pi = 6.28318530717958647692f;
+    auto re_at = [&](int t) { return t < T ? xf[size_t(t) * 2 * C + c] : 0.f; };
+    auto im_at = [&](int t) { return t < T ? xf[size_t(t) * 2 * C + C + c] : 0.f; };
+    float acc = 0.f;
+    float next = atan2f(im_at(0), re_at(0));                   // phase_0: angle of the first frame
+    for (int j = 0; j < T_out; ++j) {
+        acc = __fadd_rn(acc, next);                            // cumsum([phase_0, phase[:-1]])
+        const int a = i0[j], b = i1[j];
+        const float r0 = re_at(a), m0 = im_at(a), r1 = re_at(b), m1 = im_at(b);
+        const float n0 = sqrtf(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(m0, m0)));
+        const float n1 = sqrtf(__fadd_rn(__fmul_rn(r1, r1), __fmul_rn(m1, m1)));
+        float ph = __fadd_rn(__fadd_rn(atan2f(m1, r1), -atan2f(m0, r0)), -adv);
+        ph = __fadd_rn(ph, -__fmul_rn(two_pi, rintf(__fdiv_rn(ph, two_pi))));
+        next = __fadd_rn(ph, adv);
+        const float al = alpha[j];
+        const float mag = __fadd_rn(__fmul_rn(al, n1), __fmul_rn(__fadd_rn(1.f, -al), n0));
+        float sn, cs;
+        sincosf(acc, &sn, &cs);
+        of[size_t(j) * 2 * C + c] = __fmul_rn(mag, cs);
+        of[size_t(j) * 2 * C + C + c] = __fmul_rn(mag, sn);
+    }
+}
+
 cudaError_t launch_axis_scale(const float* x, const float* m, float* out, size_t outer, size_t n_axis,
                               size_t inner, cudaStream_t st) {
     const size_t total = outer * n_axis * inner;
@@ -394,6 +434,12 @@ cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out,
     return cudaGetLastError();
 }
 
+cudaError_t launch_phase_vocoder(const float* x, float* out, int F, int T, int C, int T_out, const int32_t* i0,
+                                 const int32_t* i1, const float* alpha, float adv_step, cudaStream_t st) {
+    if (F * C == 0 || T_out == 0) return cudaSuccess;
+    k_phase_vocoder<<<(F * C + 127) / 128, 128, 0, st>>>(x, out, F, T, C, T_out, i0, i1, alpha, adv_step);
+    return cudaGetLastError();
+}
 cudaError_t launch_sum_pool2(const float* y, float* out, int B, int T, int K, float scale, cudaStream_t st) {
     const size_t n = size_t(B) * ((T + 1) / 2) * K;
     if (n == 0) return cudaSuccess;

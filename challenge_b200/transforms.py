@@ -141,11 +141,26 @@ def magphase_to_complex(magphase):
 
 
 def phase_vocoder(complex_spec, rate=1.):
-    """transforms.py:137-195.  ``rate == 1`` is the identity like the reference; other rates
-    are outside the hot path (no trainer calls it) and not built yet."""
+    """transforms.py:137-195 -- time-stretch by ``rate`` (magnitudes interpolated between
+    neighbouring frames, phases advanced by the wrapped frame-to-frame difference).
+    ``rate == 1`` returns the input, like the reference.  The time-step arithmetic
+    (``tf.range(0, T, rate)`` in float32: ``ceil(T / rate)`` steps ``i * rate``) is done on the
+    host, the per-row phase accumulation on the GPU."""
     if rate == 1:
         return complex_spec
-    raise NotImplementedError('phase_vocoder(rate != 1) is outside the hot path (SURVEY.md 8f)')
+    x = O.dev(complex_spec)
+    if x.dim() != 3 or x.shape[-1] % 2:
+        raise ValueError('phase_vocoder expects [freq, time, chan*2]')
+    F, T, C2 = (int(v) for v in x.shape)
+    f32 = np.float32
+    n_steps = int(np.ceil(T / rate))
+    steps = (f32(0) + np.arange(n_steps, dtype=np.float32) * f32(rate)).astype(np.float32)
+    idx0, p0 = O.i32_host(steps.astype(np.int32))
+    idx1, p1 = O.i32_host((steps + f32(1)).astype(np.int32))
+    alpha, pa = O.f32_host(np.mod(steps, f32(1.)))
+    out = O.empty((F, n_steps, C2))
+    O.call('iris_op_phase_vocoder', O.ptr(x), O.ptr(out), F, T, C2 // 2, n_steps, p0, p1, pa)
+    return out
 
 
 complex_to_magphase._iris_stage = ('magphase',)

@@ -228,6 +228,14 @@ int iris_op_cos_sim(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred,
                     int B, int T, int K, iris_stream stream);
 
 
+/* transforms.phase_vocoder (transforms.py:137-195), SURVEY.md 8f rank 3: x [n_freq, T, 2*chan]
+ * -> out [n_freq, T_out, 2*chan].  idx0 / idx1 / alpha are HOST arrays [T_out] with the
+ * reference's time-step arithmetic: steps = tf.range(0, T, rate), idx0 = int32(steps),
+ * idx1 = int32(steps + 1) (frames T, T + 1 are the zero padding), alpha = steps % 1. */
+int iris_op_phase_vocoder(iris_ctx* ctx, const float* d_x, float* d_out, int n_freq, int T, int n_chan,
+                          int T_out, const int32_t* idx0, const int32_t* idx1, const float* alpha,
+                          iris_stream stream);
+
 /* ---- trainer.py label variants (trainer.py:86-104), SURVEY.md 8f rank 4 ---- */
 /* One stage of trainer.preprocess_labels: avg_pool1d(y, 2, 2, 'SAME') * 2 (* scale) on
  * y [B, T, K] -> out [B, ceil(T/2), K]; a lone last cell is doubled (TF averages over the

@@ -160,8 +160,11 @@ def phase_vocoder(complex_spec, rate=1.):
     def angle(spec):
         return np.arctan2(spec[..., n_chan:], spec[..., :n_chan])
 
-    phase_advance = np.linspace(0., np.pi * float(hop_length), freq, dtype=np.float64)
-    phase_advance = phase_advance.astype(np.float32).reshape(-1, 1, 1)
+    # tf.linspace on float32 arguments [TF-sem]: start + step * i in float32 with
+    # step = (stop - start) / (num - 1); stop = float32(pi) * hop
+    stop = f32(np.pi) * f32(hop_length)
+    step = f32(stop / f32(freq - 1))
+    phase_advance = (step * np.arange(freq, dtype=np.float32)).astype(np.float32).reshape(-1, 1, 1)
     n_t = complex_spec.shape[1]
     # tf.range(0, T, rate, dtype=float32): ceil(T/rate) elements, start + i*delta
     n_steps = int(np.ceil(n_t / rate))

@@ -336,3 +336,32 @@ def test_trainer_make_dataset_on_pickled_banks(mods, tmp_path):
         assert np.all(_np(y) >= 0)
         n += 1
     assert n == 2
+
+
+def test_phase_vocoder(mods):
+    """transforms_test.py:98-109 restated (identity at rate 1, output shapes) plus values against
+    the oracle restatement of transforms.py:137-195."""
+    from oracle import transforms as OT
+    _, TR, _, _ = mods
+    rng = np.random.default_rng(8)
+    n_freq, time, chan2 = 257, 100, 6
+    spec = rng.standard_normal((n_freq, time, chan2)).astype(np.float32)
+    assert TR.phase_vocoder(spec, 1.) is spec
+    for rate in (1.2, 0.8, 2.0, 0.5):
+        pv = _np(TR.phase_vocoder(spec, rate=rate))
+        assert pv.shape == (n_freq, int(np.ceil(time / rate)), chan2)
+        ref = OT.phase_vocoder(spec, rate)
+        C = chan2 // 2
+        # magnitudes are a plain interpolation: tight.  The accumulated phase of bin f grows by
+        # ~pi * f per step (tf.cumsum in float32, transforms.py:186): at f = 256 it reaches 1e4..1e5
+        # rad, where ONE float32 ulp is 1e-3..8e-3 rad, so a last-bit difference in any atan2 of the
+        # chain is visible at that level in cos / sin of the sum -- in the reference itself too.
+        # Bin 0 (small sums) must agree tightly, the whole tensor to two ulps of the largest
+        # accumulated phase (pi * 256 * steps): once two float32 running sums differ in the last bit,
+        # their later roundings are independent.
+        assert nmax_err(np.hypot(pv[..., :C], pv[..., C:]), np.hypot(ref[..., :C], ref[..., C:])) <= 1e-6
+        assert np.abs(pv[:1] - ref[:1]).max() <= 5e-5 * np.abs(ref).max()     # bin 0: no phase advance
+        acc_max = np.pi * 256 * pv.shape[1]
+        ulp = 2.0 ** (np.floor(np.log2(acc_max)) - 23)
+        assert nmax_err(pv, ref) <= max(1e-4, 2 * ulp)
+        assert np.median(np.abs(pv - ref)) <= 1e-5 * np.abs(ref).max()            # and typically far closer
