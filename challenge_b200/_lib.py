@@ -55,6 +55,8 @@ SIGNATURES = {
     'iris_metric_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    'iris_er_counts_pooled': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     'iris_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'iris_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i32p, C.c_int]),
     'iris_plan_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
@@ -82,6 +84,9 @@ SIGNATURES = {
                                   C.c_int, C.c_void_p]),
     'iris_op_phase_vocoder': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'iris_resample_len': (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    'iris_resample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p]),
     'iris_op_sum_pool2': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p]),
     'iris_op_density_labels': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

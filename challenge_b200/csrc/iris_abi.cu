@@ -885,9 +885,21 @@ int iris_metric_counts(iris_ctx* c, const float* y_true, const float* y_pred, in
     int rc = set_device(c);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CU(launch_metric_counts(y_true, y_pred, B, T, K, thr, d_triples,
+    CU(launch_metric_counts(y_true, y_pred, B, T, T, K, thr, d_triples,
                             reinterpret_cast<unsigned long long*>(d_tpfpfn),
                             reinterpret_cast<unsigned long long*>(d_sums), st));
+    if (d_er) CU(launch_er_finalize(d_triples, B, d_er, st));
+    return IRIS_OK;
+}
+
+int iris_er_counts_pooled(iris_ctx* c, const float* y_true, int T, const float* y_pred, int T_pred, int B,
+                          int K, float thr, int32_t* d_triples, float* d_er, iris_stream stream) {
+    if (!c || !y_true || !y_pred || !d_triples) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (B < 1 || T < 1 || T_pred < 1 || K < 1) return fail(IRIS_ERR_INVALID, "bad shape");
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(launch_metric_counts(y_true, y_pred, B, T, T_pred, K, thr, d_triples, nullptr, nullptr, st));
     if (d_er) CU(launch_er_finalize(d_triples, B, d_er, st));
     return IRIS_OK;
 }

@@ -43,7 +43,7 @@ struct LabelParams {
 cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream);
 
 // k_metrics.cu
-cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int K,
+cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int Tp, int K,
                                  float threshold, int32_t* triples, unsigned long long* tpfpfn,
                                  unsigned long long* sums, cudaStream_t stream);
 cudaError_t launch_er_finalize(const int32_t* triples, int B, float* er, cudaStream_t stream);
@@ -73,6 +73,11 @@ cudaError_t launch_phase_vocoder(const float* x, float* out, int F, int T, int C
                                  const int32_t* i1, const float* alpha, float adv_step, cudaStream_t st);
 cudaError_t launch_sum_pool2(const float* y, float* out, int B, int T, int K, float scale, cudaStream_t st);
 cudaError_t launch_density_labels(const float* y, float* out, size_t outer, int V, int TK, cudaStream_t st);
+
+// k_resample.cu -- kaldi.resample_waveform (data_utils.py:20-21)
+cudaError_t launch_resample(const float* wav, float* out, int n_chan, long long n_in, long long n_out,
+                            int u_in, int u_out, int W, const int32_t* first, const float* weights,
+                            cudaStream_t st);
 
 // k_spec.cu -- spectrogram-format banks (the reference's pickled [257, t, 2C] lists)
 cudaError_t launch_spec_activity(const float* specs, const int64_t* frame_off, int n_items, int F, int W,

@@ -1,5 +1,6 @@
 // extern "C" surface of the stand-alone stages (include/iris.h, second half): argument
 // checks, tiny host->device parameter uploads, kernel launches (k_ops.cu).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -335,6 +336,78 @@ int iris_op_phase_vocoder(iris_ctx* c, const float* x, float* out, int n_freq, i
     const float step = stop / float(n_freq - 1);
     CU(launch_phase_vocoder(x, out, n_freq, T, n_chan, T_out, di, di + T_out,
                             reinterpret_cast<const float*>(di + 2 * size_t(T_out)), step, st));
+    return IRIS_OK;
+}
+
+// torchaudio.compliance.kaldi.resample_waveform (data_utils.py:20-21): Kaldi's LinearResample.
+// The per-phase window starts and windowed-sinc weights are computed here in float32 in the
+// port's op order (kaldi.py::_get_LR_indices_and_weights), the FIR runs in k_resample.cu.
+int64_t iris_resample_len(int64_t n_in, int orig_freq, int new_freq) {
+    if (n_in <= 0 || orig_freq <= 0 || new_freq <= 0) return 0;
+    // kaldi.py::_get_num_LR_output_samples: outputs whose time lies in [0, n_in / orig_freq)
+    int64_t a = orig_freq, b = new_freq;
+    while (b) { const int64_t t = a % b; a = b; b = t; }
+    const int64_t tick = int64_t(orig_freq) / a * new_freq;
+    const int64_t ticks_in = tick / orig_freq, ticks_out = tick / new_freq;
+    const int64_t interval = n_in * ticks_in;
+    int64_t last = interval / ticks_out;
+    if (last * ticks_out == interval) --last;
+    return last + 1;
+}
+
+int iris_resample(iris_ctx* c, const float* wav, int n_chan, int64_t n_in, int orig_freq, int new_freq,
+                  float* d_out, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!wav || !d_out || n_chan < 1 || n_in < 1 || orig_freq < 1 || new_freq < 1)
+        return fail(IRIS_ERR_INVALID, "iris_resample: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (orig_freq == new_freq) {
+        CU(cudaMemcpyAsync(d_out, wav, size_t(n_in) * n_chan * 4, cudaMemcpyDefault, st));
+        return IRIS_OK;
+    }
+    int g = orig_freq;
+    for (int b = new_freq; b;) { const int t = g % b; g = b; b = t; }
+    const int u_in = orig_freq / g, u_out = new_freq / g;
+    const int min_freq = orig_freq < new_freq ? orig_freq : new_freq;
+    const double cutoff = 0.99 * 0.5 * min_freq;              // lowpass_cutoff
+    const double width = 6.0 / (2.0 * cutoff);                // window_width, lowpass_filter_width = 6
+    const float ww = float(width), fo = float(orig_freq), fn = float(new_freq);
+    std::vector<int32_t> first(u_out);
+    std::vector<float> mn(u_out);
+    int W = 0;
+    for (int i = 0; i < u_out; ++i) {
+        const float t = float(i) / fn;
+        mn[i] = ceilf((t - ww) * fo);
+        const float mx = floorf((t + ww) * fo);
+        first[i] = int32_t(mn[i]);
+        W = std::max(W, int(mx - mn[i] + 1.f));
+    }
+    if (size_t(u_out) * W > (8u << 20)) return fail(IRIS_ERR_UNSUPPORTED, "iris_resample: rate pair needs a filter bank above 32 MB");
+    std::vector<float> wt(size_t(u_out) * W);
+    const float cw = float(2 * M_PI * cutoff / 6.0), cs = float(2 * M_PI * cutoff), pi = float(M_PI);
+    for (int i = 0; i < u_out; ++i) {
+        const float t = float(i) / fn;
+        for (int j = 0; j < W; ++j) {
+            const float dt = (mn[i] + float(j)) / fo - t;
+            float w = 0.f;
+            if (fabsf(dt) < ww) w = 0.5f * (1.f + cosf(cw * dt));     // raised-cosine window
+            if (dt != 0.f) w *= sinf(cs * dt) / (pi * dt);              // sinc
+            else w *= float(2 * cutoff);
+            wt[size_t(i) * W + j] = w / fo;
+        }
+    }
+    const int64_t n_out = iris_resample_len(n_in, orig_freq, new_freq);
+    const size_t tab = size_t(u_out) * 4 + wt.size() * 4, raw = size_t(n_in) * n_chan * 4;
+    CU(c->spec_scratch.reserve(align_up(tab, 256) + raw));
+    char* base = c->spec_scratch.as<char>();
+    CU(cudaMemcpyAsync(base, first.data(), size_t(u_out) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + size_t(u_out) * 4, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice, st));
+    float* d_wav = reinterpret_cast<float*>(base + align_up(tab, 256));
+    CU(cudaMemcpyAsync(d_wav, wav, raw, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));   // the host tables are on the stack of this call
+    CU(launch_resample(d_wav, d_out, n_chan, n_in, n_out, u_in, u_out, W,
+                       reinterpret_cast<const int32_t*>(base), reinterpret_cast<const float*>(base + size_t(u_out) * 4), st));
     return IRIS_OK;
 }
 }  // extern "C"

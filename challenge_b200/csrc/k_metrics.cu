@@ -5,6 +5,10 @@
 //  * tfa F1Score(threshold=0.5, 'micro') counts (metrics.py:290-298): TP / FP / FN over the
 //    whole [B,T,K] tensor with pred = y_pred > 0.5 (strict), accumulated into 3 x uint64.
 // One CTA per sample.  Events are runs of ones in per-class bitmaps held in shared memory.
+// er_score(smoothing=True) average-pools y_pred with stride 31 first (metrics.py:222-224), so its
+// events live on a time base of Tp = ceil(T / 31) frames while y_true keeps T: the reference
+// compares the frame indices of the two bases as they are (metrics.py:256-266), and so does the
+// kernel when Tp != T (the F1 counts need equal shapes and are skipped then).
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
@@ -25,19 +29,20 @@ __device__ __forceinline__ int run_start(const uint32_t* bits, int e) {
 
 __global__ void __launch_bounds__(128) k_metric_counts(const float* __restrict__ y_true,
                                                        const float* __restrict__ y_pred, int T,
-                                                       int K, float thr, int32_t* triples,
+                                                       int Tp, int K, float thr, int32_t* triples,
                                                        unsigned long long* tpfpfn,
                                                        unsigned long long* sums) {
     extern __shared__ uint32_t s_bits[];
-    const int W = (T + 31) >> 5;
-    uint32_t* tb = s_bits;               // [K][W] y_true >= thr
-    uint32_t* pb = tb + K * W;           // [K][W] y_pred >= thr
-    uint32_t* mb = pb + K * W;           // [K][W] midpoints of predicted events
+    const int Wt = (T + 31) >> 5, Wp = (Tp + 31) >> 5;
+    const int W = max(Wt, Wp);           // one row pitch for the three bitmaps
+    uint32_t* tb = s_bits;               // [K][W] y_true >= thr (T frames)
+    uint32_t* pb = tb + K * W;           // [K][W] y_pred >= thr (Tp frames)
+    uint32_t* mb = pb + K * W;           // [K][W] midpoints of predicted events (pred time base)
     __shared__ int s_cnt[6];
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const float* yt = y_true + size_t(b) * T * K;
-    const float* yp = y_pred + size_t(b) * T * K;
+    const float* yp = y_pred + size_t(b) * Tp * K;
     for (int i = threadIdx.x; i < K * W; i += blockDim.x) mb[i] = 0u;
     if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
     int tp = 0, fp = 0, fn = 0;
@@ -45,10 +50,13 @@ __global__ void __launch_bounds__(128) k_metric_counts(const float* __restrict__
     for (int t = threadIdx.x; t < T32; t += blockDim.x) {   // warp-uniform trip count
         for (int c = 0; c < K; ++c) {
             bool a = false, q = false;
-            if (t < T) {
-                const float vt = yt[size_t(t) * K + c], vp = yp[size_t(t) * K + c];
-                a = vt >= thr;                  // metrics.py:221
+            float vp = 0.f;
+            if (t < T) a = yt[size_t(t) * K + c] >= thr;   // metrics.py:221
+            if (t < Tp) {
+                vp = yp[size_t(t) * K + c];
                 q = vp >= thr;                  // metrics.py:225
+            }
+            if (t < T && T == Tp) {
                 const bool f1p = vp > thr;      // tfa F1Score: strict
                 tp += (f1p && a);
                 fp += (f1p && !a);
@@ -153,14 +161,15 @@ __global__ void __launch_bounds__(256) k_er_finalize(const int32_t* __restrict__
     }
 }
 
-cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int K,
+cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int Tp, int K,
                                  float threshold, int32_t* triples, unsigned long long* tpfpfn,
                                  unsigned long long* sums, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    const int W = (T + 31) >> 5;
+    if (Tp != T && tpfpfn != nullptr) return cudaErrorInvalidValue;   // F1 counts need equal shapes
+    const int W = (max(T, Tp) + 31) >> 5;
     const size_t smem = size_t(3) * K * W * sizeof(uint32_t);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    k_metric_counts<<<B, 128, smem, stream>>>(y_true, y_pred, T, K, threshold, triples, tpfpfn, sums);
+    k_metric_counts<<<B, 128, smem, stream>>>(y_true, y_pred, T, Tp, K, threshold, triples, tpfpfn, sums);
     return cudaGetLastError();
 }
 

@@ -2,9 +2,10 @@
 
 Same names, argument meaning and quirks as /root/reference/data_utils.py (the broadcast in
 ``mono_chan``, the batch-axis ``[:resolution]`` slice in ``label_downsample``); tensors are
-torch CUDA tensors.  ``load_wav`` takes an in-memory waveform ``[chan, samples]`` as well as a
-file name: decoding / resampling a file is the caller-side format step,
-everything after it -- normalize, STFT, ``[freq, time, chan*2]`` layout -- is one kernel.
+torch CUDA tensors.  ``load_wav`` takes a file name (decoded by torchaudio, as in the
+reference) or an in-memory ``(waveform [chan, samples], sample_rate)`` / waveform: the kaldi
+resampler to 16 kHz (``iris_resample``), normalize, STFT and the ``[freq, time, chan*2]`` layout
+all run on the device.
 """
 import numpy as np
 
@@ -22,17 +23,19 @@ def load_wav(wav_fname):
     complex_specs: complex spectrogram of shape [freq, time, chan*2]
     (data_utils.py:9-29: normalize + Spectrogram(512, power=None) + relayout)
     '''
+    r = 16000
     if isinstance(wav_fname, (str, bytes)):
         import torchaudio
         wav, r = torchaudio.load(wav_fname)
-        if r != 16000:
-            raise NotImplementedError(
-                'load_wav: %d Hz input needs the kaldi resampler (data_utils.py:20-21), which is '
-                'outside the hot path (SURVEY.md 8f rank 2); resample to 16 kHz first' % r)
         wav = wav.numpy()
+    elif isinstance(wav_fname, tuple):
+        wav, r = wav_fname
     else:
         wav = wav_fname
-    return get_engine().stft(wav, normalize=True)
+    eng = get_engine()
+    if int(r) != 16000:
+        wav = eng.resample(wav, int(r), 16000)     # kaldi.resample_waveform (data_utils.py:20-21)
+    return eng.stft(wav, normalize=True)
 
 
 def normalize(wav):

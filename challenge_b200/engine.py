@@ -255,6 +255,23 @@ class Engine:
                                    self._ptr(out), self._stream()))
         return out
 
+    def resample(self, wav, orig_freq, new_freq=16000):
+        """``torchaudio.compliance.kaldi.resample_waveform`` (data_utils.py:20-21) on an in-memory
+        waveform ``[C, N]`` (host or device) -> ``[C, N']`` (device)."""
+        torch = _torch()
+        if isinstance(wav, torch.Tensor):
+            w = wav.to(torch.float32).contiguous()
+            ptr = w.data_ptr()
+        else:
+            w = np.ascontiguousarray(wav, np.float32)
+            ptr = w.ctypes.data
+        n_chan, n = w.shape
+        n_out = int(self.lib.iris_resample_len(n, int(orig_freq), int(new_freq)))
+        out = self._empty((n_chan, n_out))
+        L.check(self.lib.iris_resample(self._ctx, C.c_void_p(ptr), n_chan, n, int(orig_freq),
+                                       int(new_freq), self._ptr(out), self._stream()))
+        return out
+
     def metric_counts(self, y_true, y_pred, threshold=0.5, tpfpfn=None, want_er=True, counts=None):
         """-> (triples [B,3] int32, tpfpfn [3] int64 accumulated, er [B] float or None).
 
@@ -279,6 +296,22 @@ class Engine:
                                             self._ptr(tpfpfn), self._ptr(sums), self._ptr(er),
                                             self._stream()))
         return triples, tpfpfn, er
+
+
+    def er_counts_pooled(self, y_true, y_pred_pooled, threshold=0.5):
+        """``er_score(smoothing=True)`` core: ``y_pred_pooled`` is on the pooled time base
+        (metrics.py:222-224).  -> (triples [B,3] int32, er [B] float)."""
+        torch = _torch()
+        yt = torch.as_tensor(y_true, dtype=torch.float32, device=self.device).contiguous()
+        yp = torch.as_tensor(y_pred_pooled, dtype=torch.float32, device=self.device).contiguous()
+        B, T, K = yt.shape
+        assert yp.shape[0] == B and yp.shape[2] == K
+        triples = self._empty((B, 3), torch.int32)
+        er = self._empty((B,))
+        L.check(self.lib.iris_er_counts_pooled(self._ctx, self._ptr(yt), T, self._ptr(yp),
+                                               int(yp.shape[1]), B, K, float(threshold),
+                                               self._ptr(triples), self._ptr(er), self._stream()))
+        return triples, er
 
 
 _engines = {}

@@ -43,11 +43,9 @@ def er_score(threshold=0.5, smoothing=True):
             O.call('iris_op_avg_pool_time', O.ptr(yp), O.ptr(pooled), B, T, K, k, 0)
             yp = pooled
         if yt.shape != yp.shape:
-            # the reference compares frame indices of different time bases in this case
-            # (metrics.py:259-266); the counting kernel takes one frame count
-            raise NotImplementedError('er_score(smoothing=True) with T > 31 scores y_true and the '
-                                      'pooled y_pred on different time bases; use smoothing=False '
-                                      '(sj_train.py:457)')
+            # the reference compares frame indices of the two time bases as they are
+            # (metrics.py:256-266); the counting kernel keeps the two frame counts apart
+            return eng.er_counts_pooled(yt, yp, threshold=float(threshold))[1]
         _, _, er_ = eng.metric_counts(yt, yp, threshold=float(threshold))
         return er_
     return er

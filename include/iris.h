@@ -156,6 +156,16 @@ int iris_metric_counts(iris_ctx* ctx, const float* d_y_true, const float* d_y_pr
                        int n_frame, int n_classes, float threshold, int32_t* d_triples,
                        uint64_t* d_tpfpfn, uint64_t* d_sums, float* d_er, iris_stream stream);
 
+/* metrics.er_score(smoothing=True) (metrics.py:217-274): y_pred has already been average-pooled
+ * with AveragePooling1D(31, padding='same') -- strides default to the pool size, so it holds
+ * n_frame_pred = ceil(n_frame / 31) frames -- and the reference matches the midpoints of the
+ * pooled events against the un-pooled true events by their raw frame indices (metrics.py:256-266).
+ * Same integer core as iris_metric_counts with the two time bases kept apart; no F1 counts.
+ *   d_y_true [B, n_frame, K], d_y_pred [B, n_frame_pred, K]; d_triples [B,3]; d_er [B] or NULL */
+int iris_er_counts_pooled(iris_ctx* ctx, const float* d_y_true, int n_frame, const float* d_y_pred,
+                          int n_frame_pred, int batch, int n_classes, float threshold,
+                          int32_t* d_triples, float* d_er, iris_stream stream);
+
 /* Algorithmic HBM bytes of the last uploaded plan for `mode`: 4 * (samples of
  * every kept source frame range read + output elements); used by bench.py's roofline. */
 int iris_plan_bytes(iris_ctx* ctx, int mode, const uint8_t* host_keep, int64_t* bytes_in,
@@ -235,6 +245,13 @@ int iris_op_cos_sim(iris_ctx* ctx, const float* d_y_true, const float* d_y_pred,
 int iris_op_phase_vocoder(iris_ctx* ctx, const float* d_x, float* d_out, int n_freq, int T, int n_chan,
                           int T_out, const int32_t* idx0, const int32_t* idx1, const float* alpha,
                           iris_stream stream);
+
+/* torchaudio.compliance.kaldi.resample_waveform(wav, orig_freq, new_freq) as load_wav calls it
+ * (data_utils.py:20-21; Kaldi LinearResample, lowpass_filter_width 6, cutoff 0.99 * Nyquist of the
+ * lower rate).  wav [n_chan, n_in] host or device -> d_out [n_chan, iris_resample_len(...)]. */
+int64_t iris_resample_len(int64_t n_in, int orig_freq, int new_freq);
+int iris_resample(iris_ctx* ctx, const float* wav, int n_chan, int64_t n_in, int orig_freq, int new_freq,
+                  float* d_out, iris_stream stream);
 
 /* ---- trainer.py label variants (trainer.py:86-104), SURVEY.md 8f rank 4 ---- */
 /* One stage of trainer.preprocess_labels: avg_pool1d(y, 2, 2, 'SAME') * 2 (* scale) on

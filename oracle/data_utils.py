@@ -202,3 +202,90 @@ def speech_enhancement_preprocess(x, y=None):
     y = (np.sum(y[0], axis=-3), y[1][1:, ..., :x.shape[-1] // 2],
          y[2][1:, ..., :x.shape[-1] // 2])
     return x, y
+
+
+# ---- torchaudio.compliance.kaldi.resample_waveform (data_utils.py:20-21) ----
+# THIRD-PARTY ALGORITHM, not under /root/reference: torchaudio (requirements.txt:5, unpinned; the
+# reference's API usage -- Spectrogram(power=None) returning a real [..., 2] view -- implies
+# <= 0.8, where resample_waveform is the port of Kaldi's LinearResample restated below; since 0.9
+# the same filter lives in torchaudio.functional.resample, which tests/test_oracle_golden.py runs
+# here as the pin: identical window, sinc, scaling, zero padding and output length).
+def _lr_num_output_samples(input_num_samp, samp_rate_in, samp_rate_out):
+    """kaldi.py::_get_num_LR_output_samples: outputs whose time lies in [0, len / orig_freq)."""
+    import math
+    samp_in, samp_out = int(samp_rate_in), int(samp_rate_out)
+    tick_freq = samp_in * samp_out // math.gcd(samp_in, samp_out)
+    ticks_per_input_period = tick_freq // samp_in
+    interval_length_in_ticks = input_num_samp * ticks_per_input_period
+    if interval_length_in_ticks <= 0:
+        return 0
+    ticks_per_output_period = tick_freq // samp_out
+    last_output_samp = interval_length_in_ticks // ticks_per_output_period
+    if last_output_samp * ticks_per_output_period == interval_length_in_ticks:
+        last_output_samp -= 1
+    return last_output_samp + 1
+
+
+def _lr_indices_and_weights(orig_freq, new_freq, output_samples_in_unit, window_width,
+                            lowpass_cutoff, lowpass_filter_width):
+    """kaldi.py::_get_LR_indices_and_weights in float32, op for op: for every output phase the
+    first input sample of its window and the windowed-sinc weights."""
+    f32 = np.float32
+    output_t = np.arange(output_samples_in_unit, dtype=f32) / f32(new_freq)
+    min_t = output_t - f32(window_width)
+    max_t = output_t + f32(window_width)
+    min_input_index = np.ceil(min_t * f32(orig_freq))
+    max_input_index = np.floor(max_t * f32(orig_freq))
+    num_indices = max_input_index - min_input_index + 1
+    max_weight_width = int(num_indices.max())
+    j = np.arange(max_weight_width, dtype=f32)[None, :]
+    input_index = min_input_index[:, None] + j
+    delta_t = (input_index / f32(orig_freq)) - output_t[:, None]
+    weights = np.zeros_like(delta_t)
+    inside = np.abs(delta_t) < f32(window_width)
+    # raised-cosine (Hanning) window of width window_width
+    weights[inside] = f32(0.5) * (1 + np.cos(
+        f32(2 * np.pi * lowpass_cutoff / lowpass_filter_width) * delta_t[inside], dtype=f32))
+    zero = delta_t == 0
+    nz = ~zero
+    weights[nz] *= np.sin(f32(2 * np.pi * lowpass_cutoff) * delta_t[nz], dtype=f32) / (
+        f32(np.pi) * delta_t[nz])
+    weights[zero] *= f32(2 * lowpass_cutoff)
+    weights /= f32(orig_freq)
+    return min_input_index.astype(np.int64), weights.astype(f32)
+
+
+def resample_waveform(wav, orig_freq, new_freq, lowpass_filter_width=6):
+    """kaldi.resample_waveform: out[c, u*U_out + i] = sum_j w[i, j] * wav[c, first[i] + u*U_in + j],
+    zero outside the clip (the port's conv1d with stride U_in per output phase i, zero-padded)."""
+    import math
+    wav = np.asarray(wav, np.float32)
+    assert wav.ndim == 2 and orig_freq > 0 and new_freq > 0
+    if int(orig_freq) == int(new_freq):
+        return wav.copy()
+    min_freq = min(orig_freq, new_freq)
+    lowpass_cutoff = 0.99 * 0.5 * min_freq
+    assert lowpass_cutoff * 2 <= min_freq
+    base_freq = math.gcd(int(orig_freq), int(new_freq))
+    u_in = int(orig_freq) // base_freq
+    u_out = int(new_freq) // base_freq
+    window_width = lowpass_filter_width / (2.0 * lowpass_cutoff)
+    first, weights = _lr_indices_and_weights(orig_freq, new_freq, u_out, window_width,
+                                             lowpass_cutoff, lowpass_filter_width)
+    C, n_in = wav.shape
+    n_out = _lr_num_output_samples(n_in, orig_freq, new_freq)
+    W = weights.shape[1]
+    n_units = (n_out + u_out - 1) // u_out
+    lo = int(min(first.min(), 0))
+    hi = int(first.max()) + (n_units - 1) * u_in + W
+    padded = np.zeros((C, max(hi, n_in) - lo), np.float32)
+    padded[:, -lo:-lo + n_in] = wav
+    out = np.zeros((C, n_units * u_out), np.float32)
+    units = np.arange(n_units) * u_in
+    for i in range(u_out):
+        acc = np.zeros((C, n_units), np.float32)
+        base = units + int(first[i]) - lo
+        for jj in range(W):
+            acc += weights[i, jj] * padded[:, base + jj]
+        out[:, i::u_out] = acc
+    return out[:, :n_out]

@@ -179,6 +179,26 @@ def test_label_downsample(mods, T, r):
     assert got[1:] == ('a', 'b') and np.array_equal(_np(got[0]), ref)
 
 
+@pytest.mark.parametrize('orig,n', [(44100, 22051), (48000, 30001), (8000, 9000), (22050, 12345),
+                                    (32000, 4000), (16000, 700)])
+def test_load_wav_resamples_like_kaldi(mods, orig, n):
+    """data_utils.load_wav on audio that is not 16 kHz (data_utils.py:19-22): the kaldi resampler on
+    the device against the oracle restatement, then the whole load_wav against the oracle chain."""
+    from challenge_b200.engine import get_engine
+    from oracle import data_utils as OD
+    _, _, D, _ = mods
+    rng = np.random.default_rng(orig)
+    wav = (rng.standard_normal((2, n)) * 0.1).astype(np.float32)
+    ref = OD.resample_waveform(wav, orig, 16000)
+    got = _np(get_engine().resample(wav, orig, 16000))
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()      # fp32 FIR, different summation order
+    spec = _np(D.load_wav((wav, orig)))
+    ref_spec = OD.load_wav_array(ref)
+    assert spec.shape == ref_spec.shape
+    assert np.abs(spec - ref_spec).max() <= 1e-4 * np.abs(ref_spec).max()
+
+
 # ---- metrics_test.py ----
 def test_er_score(mods):
     _, _, _, MT = mods
@@ -192,6 +212,29 @@ def test_er_score(mods):
     er = MT.er_score(smoothing=False)(g, p)
     assert float(_np(er).mean()) == np.float32(k['mean_er'])      # metrics_test.py:25
     assert _np(MT.er_counts(g, p)).tolist() == [[5, 5, 2], [5, 5, 2]]
+
+
+@pytest.mark.parametrize('T', [20, 31, 626, 1000])
+def test_er_score_smoothing_pooled_time_base(mods, T):
+    """er_score(smoothing=True) (metrics.py:222-224): AveragePooling1D(31, 'same') has stride 31,
+    so the predicted events live on ceil(T / 31) frames while the true events keep T; the
+    reference matches them by raw frame index and so does iris_er_counts_pooled."""
+    from oracle import metrics as OM
+    _, _, _, MT = mods
+    rng = np.random.default_rng(T)
+    B = 24
+    yt = np.zeros((B, T, 3), np.float32)
+    for b in range(B):                       # a few events per class, some near frame 0 so that
+        for c in range(3):                   # pooled midpoints (< ceil(T/31)) can fall inside them
+            for _ in range(int(rng.integers(0, 4))):
+                s = int(rng.integers(0, max(T // 4, 1)))
+                yt[b, s:s + int(rng.integers(1, 30)), c] = 1
+    yp = np.clip(yt + rng.normal(0, 0.3, yt.shape), 0, 1).astype(np.float32)
+    got = _np(MT.er_score(smoothing=True)(yt, yp))
+    ref = OM.er_score(smoothing=True)(yt, yp)
+    nt, npd, co = OM.er_parts(yt, yp, 0.5, True)
+    assert co.sum() > 0 or T <= 31
+    np.testing.assert_array_equal(got, ref)
 
 
 def test_f1_and_cos_sim(mods):

@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from oracle import data_utils as D
 from oracle import metrics as M
@@ -201,3 +202,20 @@ def test_f1_and_cos_sim():
     assert (f.tp, f.fp, f.fn) == (4, 4, 2)      # never reset (metrics.py:291-297)
     cs = M.cos_sim(y, y)
     assert np.isclose(cs[0], -1.0) and cs[1] == 0
+
+
+@pytest.mark.parametrize('orig,n', [(44100, 22051), (48000, 30001), (8000, 9000), (22050, 12345)])
+def test_oracle_resampler_is_pinned_to_torchaudio(orig, n):
+    """The reference calls torchaudio.compliance.kaldi.resample_waveform (data_utils.py:20-21), gone
+    from torchaudio 2.x; the same filter (Hann-windowed sinc, width 6, cutoff 0.99 Nyquist, zero
+    padding, ceil(len * new / orig) outputs) is torchaudio.functional.resample, run here as the
+    pin of the oracle's restatement of the Kaldi port."""
+    torch = pytest.importorskip('torch')
+    ta = pytest.importorskip('torchaudio')
+    from oracle import data_utils as OD
+    rng = np.random.default_rng(orig)
+    wav = rng.standard_normal((2, n)).astype(np.float32)
+    got = OD.resample_waveform(wav, orig, 16000)
+    ref = ta.functional.resample(torch.from_numpy(wav), orig, 16000).numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
