@@ -124,6 +124,7 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
 int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
     p.max_segs = max_segs < 1 ? 1 : max_segs;
     p.stage_out = fused_stages_output(mode, p.remap, p.fr) && !getenv("IRIS_NO_STAGE") ? 1 : 0;
+    p.pair_merge = p.stage_out && p.C == 4 && !getenv("IRIS_NO_PAIR_MERGE") ? 1 : 0;
     p.l2_hints = getenv("IRIS_NO_L2_HINTS") ? 0 : 1;   // measured: min-max log-mel 255 -> 250 us
     int stride = 0;
     const size_t bytes = fused_tile_bytes(p, &stride);
@@ -136,6 +137,7 @@ int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t 
         const int v = atoi(e);
         if (v >= 1 && v <= 4096) p.chunk = v;
     }
+    if (p.pair_merge && (p.chunk & 1)) ++p.chunk;   // both pairs of a (clip, time) range in one work claim
     CU(launch_fused(p, mode, c->num_sms, st));
     return IRIS_OK;
 }

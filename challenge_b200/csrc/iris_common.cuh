@@ -62,6 +62,7 @@ struct FusedParams {
     // outputs
     float* out;             // layout depends on mode
     int32_t stage_out;      // spectrogram modes: store through the shared-memory staging area
+    int32_t pair_merge;     // stage_out with C == 4: the two channel pairs of a tile are stored together
     int32_t l2_hints;       // L2 eviction hints on the bank stream / the mel rows
     uint8_t* activity;      // FM_ACTIVITY: [B, T]
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log

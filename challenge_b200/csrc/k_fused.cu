@@ -588,20 +588,50 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 // ---- spectrogram modes: every warp parks the 257 x 16 B pieces of its frame in
                 // the staging area, then the 8 warps store bin rows of 8 frames = 128 B each ----
                 float4* stg = reinterpret_cast<float4*>(slots + S * slotB);
+                // 4-channel clips (p.pair_merge): the two channel pairs of a (clip, time) range are
+                // consecutive tiles of one CTA.  Pair 0 only parks its pieces in the staging area;
+                // pair 1 parks its own in the warp's (now idle) exchange rows -- bin f of frame j at
+                // 16-byte position f ^ j, so that the 8 frames of a bin fall into 8 distinct bank
+                // groups -- and the store phase writes whole 32-byte cells [re0..re3 | im0..im3]:
+                // 8 frames = 256 contiguous bytes per bin instead of four 8-byte pieces per cell
+                // written by two different tiles.
+                const bool merge = p.pair_merge != 0;
+                float4* park = (merge && pair == 1) ? reinterpret_cast<float4*>(xch) : stg;
                 if (do_fft) {
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
                         const int f = k1 + 16 * (2 * jj + par);
                         const cpx zf = u[jj], zm = mirror(jj);
-                        stg[f * FR + (j ^ (f & 7))] =
+                        const int pos = (merge && pair == 1) ? (f ^ j) : f * FR + (j ^ (f & 7));
+                        park[pos] =
                             make_piece<MODE>(p, f, zf.x + zm.x, zf.y - zm.y, zf.y + zm.y, zm.x - zf.x,
                                              ((zbits >> jj) & 1u) ? 0.f : mt);
                     }
                     if (l0) {
                         const cpx zf = u[8];
-                        stg[256 * FR + j] = make_piece<MODE>(p, 256, zf.x + zf.x, zf.y - zf.y, zf.y + zf.y,
-                                                             zf.x - zf.x, ((zbits >> 8) & 1u) ? 0.f : mt);
+                        const int pos = (merge && pair == 1) ? (256 ^ j) : 256 * FR + j;
+                        park[pos] = make_piece<MODE>(p, 256, zf.x + zf.x, zf.y - zf.y, zf.y + zf.y,
+                                                     zf.x - zf.x, ((zbits >> 8) & 1u) ? 0.f : mt);
                     }
+                }
+                if (merge) {
+                    if (pair == 1) {   // warp-uniform (tile header)
+                        named_bar_sync(1, FR * 32);
+                        const int jt = lane & 7, half = (lane >> 3) & 1;
+                        const int tt = (hdr.z & 0xffffff) + jt;
+                        if (tt < p.T) {
+                            const unsigned char* x1 = sm + off_xch(p.mel_taps) + jt * kXwBytes + half * 8;
+                            const unsigned char* x0 = reinterpret_cast<const unsigned char*>(stg) + half * 8;
+                            float* o = p.out + (size_t(b) * kBins * p.T + tt) * 8 + half * 4;
+                            for (int f = warp * 2 + (lane >> 4); f < kBins; f += FR * 2) {
+                                const float2 a = *reinterpret_cast<const float2*>(x0 + (f * FR + (jt ^ (f & 7))) * 16);
+                                const float2 c = *reinterpret_cast<const float2*>(x1 + ((f ^ jt) << 4));
+                                *reinterpret_cast<float4*>(o + size_t(f) * p.T * 8) = make_float4(a.x, a.y, c.x, c.y);
+                            }
+                        }
+                        named_bar_sync(1, FR * 32);   // staging + exchange rows are read before they are reused
+                    }
+                    continue;
                 }
                 named_bar_sync(1, FR * 32);
                 {

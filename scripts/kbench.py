@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel micro-benchmark: times iris_features() (k_tiles + k_fused) per mode with CUDA events.
-usage: python scripts/kbench.py [B] [iters]"""
+usage: python scripts/kbench.py [B] [iters] [C: only this channel count]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -24,7 +24,8 @@ def timeit(fn, n=iters):
         ts.append(a.elapsed_time(b) * 1e3)
     return float(np.median(ts)), float(np.min(ts))
 
-for C in (2, 4):
+only_c = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for C in ((only_c,) if only_c else (2, 4)):
     bgs, voices, labels, noises = synthetic_banks(20202, C, 64, 256, 64)
     bf = eng.register_bank(L.BANK_BG, bgs); vf = eng.register_bank(L.BANK_VOICE, voices, labels=labels)
     nf = eng.register_bank(L.BANK_NOISE, noises)

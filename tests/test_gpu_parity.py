@@ -119,6 +119,12 @@ def test_cfg3_four_channel_magphase_labels(engine, workload_factory):
     assert got.shape == ref.shape == (4, 257, 626, 8)
     assert nmax_err(got[..., :4], ref[..., :4]) < TOL
     assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    got_c = engine.features(L.FEAT_COMPLEX).cpu().numpy()     # both channel pairs stored as 32-byte cells
+    ref_c = _oracle(w, d, mode='complex')[0]
+    assert got_c.shape == ref_c.shape == (4, 257, 626, 8)
+    assert nmax_err(got_c, ref_c) < TOL
+    for ch in range(8):                                       # every channel lands in its own column
+        assert nmax_err(got_c[..., ch], ref_c[..., ch]) < 10 * TOL, ch
     got = engine.features(L.FEAT_LOG_MAGPHASE).cpu().numpy()
     ref = _oracle(w, d, mode='log_magphase')[0]
     sel = ref[..., :4] > np.log(1e-3 * np.exp(ref[..., :4].max()))
