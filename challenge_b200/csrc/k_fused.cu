@@ -29,6 +29,9 @@
 //    source row enters the SM once per tile.
 //  * LOGMEL_MINMAX: per-warp min/max go to global atomics; k_logmel_post (k_post.cu)
 //    normalises and logs the batch in place right after, while it is still in L2.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fftwarp.cuh"
 #include "iris_common.cuh"
 #include "iris_epilogue.cuh"
@@ -705,22 +708,41 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
-    const int per_sm = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
-    const long long max_ctas = (long long)num_sms * per_sm;
-    const int grid = int(n_tiles < max_ctas ? n_tiles : max_ctas);
     const int threads = (FR + 1) * 32;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    // persistent grid: as many CTAs as are resident at once, asked of the occupancy calculator once
+    // per kernel variant.  The register cap decides between 1 and 2 CTAs per SM: measured on B200,
+    // 96 registers give 2 x 9 warps, 104 and 112 only one CTA (576 x 112 = 64512 < 65536, but
+    // registers are granted per warp in larger units) -- 4-ch COMPLEX 570 -> 730 us, mel 200 -> 265 us.
 #define IRIS_LAUNCH(M, NJV)                                                                     \
     {                                                                                           \
-        static bool attr_set = false;                                                           \
-        if (!attr_set) {                                                                        \
+        static int attr_dev = -1;   /* function attributes are per device */                    \
+        static int per_sm = 1;                                                                  \
+        static size_t per_sm_smem = 0;                                                          \
+        if (attr_dev != dev) {                                                                  \
             cudaError_t e = cudaFuncSetAttribute(k_fused<M, NJV>,                               \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                                  227 * 1024);                                   \
             if (e != cudaSuccess) return e;                                                     \
             cudaFuncSetAttribute(k_fused<M, NJV>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                  cudaSharedmemCarveoutMaxShared);                               \
-            attr_set = true;                                                                    \
+            attr_dev = dev;                                                                     \
+            per_sm_smem = 0;                                                                    \
         }                                                                                       \
+        if (per_sm_smem != smem) {                                                              \
+            int nb = 0;                                                                         \
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused<M, NJV>, \
+                                                                          threads, smem);       \
+            if (e != cudaSuccess) return e;                                                     \
+            per_sm = nb < 1 ? 1 : nb;                                                           \
+            per_sm_smem = smem;                                                                 \
+            if (getenv("IRIS_VERBOSE"))                                                         \
+                fprintf(stderr, "k_fused<%d,%d>: %d CTAs/SM (%zu B smem, %d threads)\n", int(M), \
+                        NJV, per_sm, smem, threads);                                            \
+        }                                                                                       \
+        const long long max_ctas = (long long)num_sms * per_sm;                                 \
+        const int grid = int(n_tiles < max_ctas ? n_tiles : max_ctas);                          \
         k_fused<M, NJV><<<grid, threads, smem, stream>>>(p);                                    \
     }
     switch (mode) {
