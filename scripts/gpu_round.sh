@@ -25,5 +25,7 @@ ncu)
      -f -o gpurun_out/prof_fused python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e \
      > gpurun_out/ncu_bench.log 2>&1
   tail -2 gpurun_out/ncu_bench.log ;;
+kbench)
+  timeout 600 python scripts/kbench.py 256 10 2>&1 | grep "C=" | tee gpurun_out/kbench.log ;;
 esac
 done
