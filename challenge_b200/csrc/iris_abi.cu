@@ -124,6 +124,7 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
 int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
     p.max_segs = max_segs < 1 ? 1 : max_segs;
     p.stage_out = fused_stages_output(mode, p.remap, p.fr) && !getenv("IRIS_NO_STAGE") ? 1 : 0;
+    p.fm_bits = (mode == FM_MEL && p.mel_f_lo + p.mel_f_n <= 128) ? 1 : 0;   // = the NJ == 4 kernels
     p.pair_merge = p.stage_out && p.C == 4 && !getenv("IRIS_NO_PAIR_MERGE") ? 1 : 0;
     p.l2_hints = getenv("IRIS_NO_L2_HINTS") ? 0 : 1;   // measured: min-max log-mel 255 -> 250 us
     int stride = 0;

@@ -48,6 +48,8 @@ struct FusedParams {
     const int32_t* fmask;
     int32_t n_fmask;
     int32_t filter_k;  // stft_filter: zero bins 1..k
+    int32_t fm_bits;   // k_tiles writes the zeroed bins 0..127 of a tile as a bitmap instead of the
+                       // (size, offset) list (mel epilogues that read bins below 128 only)
     int32_t remap;
     const float* merge_f;   // [B, c_out-2] factor
     const float* merge_sf;  // [B, c_out-2] sqrt(1-factor)

@@ -158,17 +158,32 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
     int4 hdr;
     hdr.x = n; hdr.y = b; hdr.z = t0 | (pair << 24); hdr.w = int(tbits);
     *reinterpret_cast<int4*>(blk) = hdr;
-    int16_t fm[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) fm[i] = 0;
-    if (p.fmask != nullptr) {
-        const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
-        for (int i = 0; i < p.n_fmask && i < 4; ++i) {
-            fm[2 * i] = int16_t(fk[2 * i]);
-            fm[2 * i + 1] = int16_t(fk[2 * i + 1]);
+    if (p.fm_bits) {
+        // mel epilogues that need bins below 128 only: the bins zeroed by the frequency masks and
+        // stft_filter as a 128-bit map, so that a lane picks up its four bits with four shifts
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        auto zero_bins = [&](int off, int size) {
+            for (int f = max(off, 0); f < min(off + size, 128); ++f) w[f >> 5] |= 1u << (f & 31);
+        };
+        if (p.fmask != nullptr) {
+            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
+            for (int i = 0; i < p.n_fmask; ++i) zero_bins(fk[2 * i + 1], fk[2 * i]);
         }
+        if (p.filter_k > 0) zero_bins(1, p.filter_k);
+        *reinterpret_cast<uint4*>(blk + 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        int16_t fm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fm[i] = 0;
+        if (p.fmask != nullptr) {
+            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
+            for (int i = 0; i < p.n_fmask && i < 4; ++i) {
+                fm[2 * i] = int16_t(fk[2 * i]);
+                fm[2 * i + 1] = int16_t(fk[2 * i + 1]);
+            }
+        }
+        *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
     }
-    *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
 }
 
 // one (bin, frame, channel pair) of the spectrogram modes without a channel remap:
@@ -387,7 +402,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
 
         uint32_t slot = 0, phase = 0;
         const uint64_t pol_keep = l2_policy_evict_last();
-        const bool keep_l2 = kMel && p.l2_hints && do_minmax;   // re-read by k_logmel_post
+        // mel rows are re-read by k_logmel_post: keep them in L2 (fixed variants: hints are on)
+        const bool keep_l2 = kFix ? bool(EPI & EPI_MINMAX) : (kMel && p.l2_hints && do_minmax);
+        float* clip_out = p.out;      // out[b, m = lane, 0, 0] of the current clip (mel modes)
         uint32_t zbits = 0;
         int zb_clip = -1;
         const size_t lane_off = size_t(lane) * p.T * C;          // out[b, m = lane + 32 r, t, c]
@@ -447,8 +464,16 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             // bit 8 -> bin 256.  Recomputed when the clip changes.
             if (b != zb_clip) {
                 zb_clip = b;
+                if (kMel) clip_out = p.out + size_t(b) * clip_elems + lane_off;
                 zbits = 0;
                 const int4 fmv = *reinterpret_cast<const int4*>(tb->fm);
+                if (kMel && NJ == 4) {
+                    // k_tiles left a bitmap of the zeroed bins 0..127 (p.fm_bits): bin
+                    // k1 + 16 par + 32 jj is bit k1 + 16 par of word jj
+                    const int sh = k1 + 16 * par;
+                    zbits = ((uint32_t(fmv.x) >> sh) & 1u) | (((uint32_t(fmv.y) >> sh) & 1u) << 1) |
+                            (((uint32_t(fmv.z) >> sh) & 1u) << 2) | (((uint32_t(fmv.w) >> sh) & 1u) << 3);
+                } else {
                 const int fmw[4] = {fmv.x, fmv.y, fmv.z, fmv.w};   // size | offset << 16
 #pragma unroll
                 for (int q = 0; q <= 4; ++q) {
@@ -460,6 +485,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                     for (int jj = 0; jj < NJ; ++jj)
                         if (unsigned(k1 + 16 * (2 * jj + par) - off) < unsigned(size)) zbits |= 1u << jj;
                     if (NJ == 8 && unsigned(256 - off) < unsigned(size)) zbits |= 1u << 8;
+                }
                 }
             }
 
@@ -554,17 +580,19 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         acc1[r] = sacc.y;
                         wr += 32 * L;
                     }
-                    __syncwarp();   // mags are consumed before the next frame's exchange
+                    // (the mags are consumed before the next frame's exchange writes: the
+                    // __syncwarp() of the next tile's first mixing stage lies in between)
                 }
                 // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
                 if (in_range) {
-                    float* o = p.out + size_t(b) * clip_elems + lane_off + size_t(t) * C + 2 * pair;
+                    float* o = clip_out + t * C + 2 * pair;
                     const size_t rs32 = size_t(32) * p.T * C;
                     const bool lg = do_lg;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         if (kFix ? (fixed_mel_L(r) == 0) : (32 * r >= p.n_mel)) break;   // uniform: no work behind the last round
-                        if (lane + 32 * r < p.n_mel) {
+                        // fixed variants: 64 < n_mel <= 96, only the third round is partial
+                        if ((kFix && r < 2) || lane + 32 * r < p.n_mel) {
                             float a0 = acc0[r], a1 = acc1[r];
                             if (do_minmax) {
                                 mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
@@ -766,7 +794,8 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
         case FM_MEL:
             if (p.mel_f_lo + p.mel_f_n > 128) IRIS_LAUNCH(FM_MEL, 8, 0)
             else if (p.C != 2 || p.mel_L[0] != fixed_mel_L(0) || p.mel_L[1] != fixed_mel_L(1) ||
-                     p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) || getenv("IRIS_NO_FIXED_EPI"))
+                     p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) || p.n_mel <= 64 ||
+                     !p.l2_hints || getenv("IRIS_NO_FIXED_EPI"))
                 IRIS_LAUNCH(FM_MEL, 4, 0)
             else if (p.do_minmax) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_MINMAX)
             else if (p.do_log) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_LOG)
