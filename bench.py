@@ -267,6 +267,8 @@ def run_gpu_arm(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    from challenge_b200.dist import bind_to_gpu_numa
+    numa_cores = bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -300,25 +302,41 @@ def run_gpu_arm(args):
 
     side = torch.cuda.Stream(device=dev)
     ev_lab = torch.cuda.Event()
-    ev_met = torch.cuda.Event()
+    ev_met = [torch.cuda.Event() for _ in range(2)]
+    met_pending = [False, False]
 
     def device_step(i, out):
         """labels -> {fused features  ||  metric counts (+ count all-reduce)}: the counting only
-        needs the frame labels, so it runs on a second stream beside the feature kernel and
-        the step ends when both are done."""
+        needs the frame labels, so it runs on a second stream beside the feature kernel.  On one
+        GPU the step ends when both are done.  With several ranks the count all-reduce is also a
+        rendezvous of the ranks, so a step waits for the collective of the step BEFORE it (the
+        reduced counts are consumed one step late, like a logged Keras metric); `drain_counts`
+        waits for the last one inside the timed region."""
         main = torch.cuda.current_stream()
         frame, _, _ = eng.labels(want_keep=False)
         ev_lab.record(main)
+        j = i & 1
         with torch.cuda.stream(side):
             side.wait_event(ev_lab)
             eng.metric_counts(frame, y_pred, counts=counts[i], want_er=False)
             if world > 1:
                 dist.all_reduce(counts[i])                  # NCCL sum of the int64 count vector
-            ev_met.record(side)
+            ev_met[j].record(side)
+            met_pending[j] = True
             frame.record_stream(side)
         eng.features(L.FEAT_LOGMEL_MINMAX, out=out)
-        main.wait_event(ev_met)
-        return frame
+        k = j if world == 1 else j ^ 1
+        if met_pending[k]:
+            main.wait_event(ev_met[k])
+            met_pending[k] = False
+        return frame, ev_met[j]
+
+    def drain_counts():
+        main = torch.cuda.current_stream()
+        for k in range(2):
+            if met_pending[k]:
+                main.wait_event(ev_met[k])
+                met_pending[k] = False
 
     # ---- kernel-resident timing: plan already uploaded, CUDA events per step ----
     plans = [draw() for _ in range(n_all)]
@@ -340,6 +358,8 @@ def run_gpu_arm(args):
         flush.fill_(s & 0xff)                               # evict L2 (untimed)
         ev[s][0].record()
         device_step(args.warmup + s, feat[0])
+        if s == args.steps - 1:
+            drain_counts()                                  # the last collective ends inside the timed region
         ev[s][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -369,24 +389,27 @@ def run_gpu_arm(args):
     copied = [torch.cuda.Event() for _ in range(2)]
     h2d = d2h = 0
 
-    def e2e_step(i):
+    def e2e_step(i, features_to_host=True):
         nonlocal h2d, d2h
         j = i & 1
         row = n_all + i
         d = draw()                                          # host randomness (numpy)
         torch.cuda.current_stream().wait_event(copied[j])   # buffer j is free again
         info = eng.upload_plan(d)                           # H2D of the draws (pinned staging)
-        frame = device_step(row, feat[j])
+        frame, counted = device_step(row, feat[j])
         done[j].record()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done[j])
-            h_feat[j].copy_(feat[j], non_blocking=True)
+            copy_stream.wait_event(counted)                 # this step's (all-reduced) counts
+            if features_to_host:
+                h_feat[j].copy_(feat[j], non_blocking=True)
             h_lbl[j].copy_(frame, non_blocking=True)
             h_cnt[j].copy_(counts[row], non_blocking=True)
             copied[j].record()
             frame.record_stream(copy_stream)
-        h2d = info['bytes']
-        d2h = h_feat[j].numel() * 4 + h_lbl[j].numel() * 4 + h_cnt[j].numel() * 8
+        if features_to_host:
+            h2d = info['bytes']
+            d2h = h_feat[j].numel() * 4 + h_lbl[j].numel() * 4 + h_cnt[j].numel() * 8
 
     n_e2e = 0 if args.no_e2e else args.steps
     n_e2e_warm = 0 if args.no_e2e else max(args.warmup, 3)
@@ -405,6 +428,22 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * n_e2e / float(t.item())
+    # the same loop with the features left on the device (what a Keras / torch model fed through
+    # DLPack sees: INTEGRATION.md section 3); labels and counts still go to the host.  Context for
+    # the PCIe-bound number above, not the e2e value.
+    for i in range(min(n_e2e_warm, 2)):
+        e2e_step(i, features_to_host=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(i, features_to_host=False)
+    torch.cuda.synchronize()
+    t = torch.tensor([max(time.perf_counter() - t0, 1e-9)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_dev_value = world * B * n_e2e / float(t.item())
 
     peak, peak_src = measured_peak()
     fused_avg_ms = fused_ms / max(n_fused, 1)
@@ -420,7 +459,10 @@ def run_gpu_arm(args):
                 'note': 'host draws (numpy) -> iris_plan_upload (H2D) -> kernels -> features + '
                         'labels + counts copied to pinned host memory; wall clock; the D2H of '
                         'step i overlaps the kernels of step i+1; PCIe-bound (features are '
-                        '400 KB per clip)'},
+                        '400 KB per clip)',
+                'features_on_device_value': e2e_dev_value,
+                'features_on_device_note': 'same loop, features handed over on the device (DLPack) '
+                                           'instead of copied to the host; labels + counts still read back'},
         'kernels_per_step': KERNELS,
         'roofline': {'bound': 'hbm', 'kernel': 'k_fused<FM_MEL> (+ k_tiles)', 'achieved': achieved,
                      'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
@@ -429,9 +471,13 @@ def run_gpu_arm(args):
                      'algorithmic_bytes_per_launch': int(alg_bytes),
                      'kernel_ms': fused_avg_ms, 'kernel_share_of_step': fused_ms / total_ms},
     }
+    if world > 1:
+        out['config']['host_binding'] = ('each rank pinned to the %d cores NVML lists for its GPU' % len(numa_cores)
+                                         if numa_cores else 'none (NVML affinity not available)')
+        out['config']['count_allreduce'] = 'one NCCL all-reduce of int64[6] per step on a side stream; a step waits for the collective of the previous step, the last one is drained inside the timed region'
     out['gpu_launches'] = int(args.steps * (len(KERNELS) + (1 if world > 1 else 0)))
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg is timed at N = 1 only
             out['cpu_baseline'] = cpu_baseline()
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -10,6 +10,36 @@ in the same collective as the ``[TP, FP, FN]`` vector.
 import numpy as np
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU ``device_index`` -- call it
+    before the first pinned allocation: one process per GPU, each on its GPU's NUMA node, so that
+    the pinned staging buffers of the plan uploads and of the feature read-back are node-local
+    and the ranks of one box do not all write into one socket's memory.  Returns the core list,
+    or None when NVML / the affinity call is not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(device_index)
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if idx < len(ids) and ids[idx].isdigit():
+                idx = int(ids[idx])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(c for c in cores if c in allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def shard_range(global_batch, world_size, rank):
     """Contiguous clip range ``[lo, hi)`` of ``rank`` (remainder spread over the first ranks)."""
     base, rem = divmod(int(global_batch), int(world_size))
