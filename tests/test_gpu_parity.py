@@ -245,6 +245,28 @@ def test_metric_counts_bit_exact(engine):
     assert tuple(tpfpfn.cpu().numpy().tolist()) == tuple(2 * v for v in M.f1_counts(yt, yp))
 
 
+@pytest.mark.parametrize('stft_filter', [0, 3])
+def test_fixed_epilogue_instances_equal_the_generic_kernel(engine, workload_factory, monkeypatch, stft_filter):
+    """The 2-channel mel modes run kernel instances whose epilogue switches are template constants
+    (k_fused<FM_MEL, 4, EPI_*>); IRIS_NO_FIXED_EPI routes the same launch through the generic
+    instance.  Same arithmetic in the same order: the outputs must be bit-identical, with masks,
+    stft_filter and a clip count that makes every CTA change clips mid-claim."""
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    d = _draw(w, 24, 626, seed=909)
+    engine.upload_plan(d, stft_filter=stft_filter)
+    engine.labels()
+    for mode in (L.FEAT_MEL, L.FEAT_LOGMEL, L.FEAT_LOGMEL_MINMAX):
+        monkeypatch.delenv('IRIS_NO_FIXED_EPI', raising=False)
+        fixed = engine.features(mode).cpu().numpy()
+        monkeypatch.setenv('IRIS_NO_FIXED_EPI', '1')
+        generic = engine.features(mode).cpu().numpy()
+        monkeypatch.delenv('IRIS_NO_FIXED_EPI', raising=False)
+        assert np.array_equal(fixed, generic), mode
+    ref = _oracle(w, d, mode='logmel_minmax', stft_filter=stft_filter)[0]
+    assert nmax_err(engine.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy(), ref) < TOL
+
+
 def test_full_size_properties_cfg2(engine, workload_factory):
     """BASELINE config 2 at full batch (256): size-independent properties + spot parity."""
     from challenge_b200 import _lib as L
