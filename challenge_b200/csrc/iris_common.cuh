@@ -218,6 +218,33 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
     if (__float_as_uint(x) >> 31) r = 3.14159265358979324f - r;
     return copysignf(r, y);
 }
+// two atan2 at once: the octant reduction and the sign fix-ups stay scalar, the degree-17 polynomial
+// runs on packed pairs (FMUL2 / FFMA2: 10 instructions for both instead of 20).  Same operations in
+// the same order as fast_atan2f, so the results are bit-identical to two scalar calls.
+__device__ __forceinline__ void fast_atan2f_x2(float y0, float x0, float y1, float x1, float& r0, float& r1) {
+    const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float hi0 = fmaxf(ax0, ay0), lo0 = fminf(ax0, ay0);
+    const float hi1 = fmaxf(ax1, ay1), lo1 = fminf(ax1, ay1);
+    const cpx a{hi0 > 0.f ? __fdividef(lo0, hi0) : 0.f, hi1 > 0.f ? __fdividef(lo1, hi1) : 0.f};
+    const cpx s = cmul2(a, a);
+    cpx r{0.0028662257f, 0.0028662257f};
+    r = cfma2(r, s, cpx{-0.0161657367f, -0.0161657367f});
+    r = cfma2(r, s, cpx{0.0429096138f, 0.0429096138f});
+    r = cfma2(r, s, cpx{-0.0752896400f, -0.0752896400f});
+    r = cfma2(r, s, cpx{0.1065626393f, 0.1065626393f});
+    r = cfma2(r, s, cpx{-0.1420889944f, -0.1420889944f});
+    r = cfma2(r, s, cpx{0.1999355085f, 0.1999355085f});
+    r = cfma2(r, s, cpx{-0.3333314528f, -0.3333314528f});
+    r = cfma2(r, s, cpx{1.0f, 1.0f});
+    r = cmul2(r, a);
+    float q0 = r.x, q1 = r.y;
+    if (ay0 > ax0) q0 = 1.57079632679489662f - q0;
+    if (ay1 > ax1) q1 = 1.57079632679489662f - q1;
+    if (__float_as_uint(x0) >> 31) q0 = 3.14159265358979324f - q0;
+    if (__float_as_uint(x1) >> 31) q1 = 3.14159265358979324f - q1;
+    r0 = copysignf(q0, y0);
+    r1 = copysignf(q1, y1);
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

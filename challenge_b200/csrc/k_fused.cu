@@ -215,9 +215,8 @@ __device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float 
     float a0 = r0, a1 = r1, b0 = i0, b1 = i1;
     if (MODE != FM_COMPLEX) {
         a0 = sqrt_approx(fmaf(r0, r0, i0 * i0));   // transforms.py:116
-        b0 = fast_atan2f(i0, r0);                  // transforms.py:117
         a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
-        b1 = fast_atan2f(i1, r1);
+        fast_atan2f_x2(i0, r0, i1, r1, b0, b1);    // transforms.py:117
         if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
             a0 = logf(a0 + 1e-8f);
             a1 = logf(a1 + 1e-8f);
