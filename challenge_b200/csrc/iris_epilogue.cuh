@@ -25,8 +25,8 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
             a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
             b1 = fast_atan2f(i1, r1);
             if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
-                a0 = logf(a0 + 1e-8f);
-                a1 = logf(a1 + 1e-8f);
+                a0 = __logf(a0 + 1e-8f);   // MUFU.LG2 * ln 2, as in the log-mel epilogue (|error| ~1e-6)
+                a1 = __logf(a1 + 1e-8f);
             }
         }
         if (C == 2) {
@@ -62,7 +62,7 @@ __device__ __forceinline__ void store_bin(const FusedParams& p, int b, int f, in
             if (MODE != FM_COMPLEX) {
                 a = sqrt_approx(fmaf(re, re, im * im));
                 ph = fast_atan2f(im, re);
-                if (MODE == FM_LOGMAGPHASE) a = logf(a + 1e-8f);
+                if (MODE == FM_LOGMAGPHASE) a = __logf(a + 1e-8f);
             }
             o[c] = a;
             o[Co + c] = ph;

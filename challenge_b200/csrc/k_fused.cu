@@ -218,8 +218,8 @@ __device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float 
         a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
         fast_atan2f_x2(i0, r0, i1, r1, b0, b1);    // transforms.py:117
         if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
-            a0 = logf(a0 + 1e-8f);
-            a1 = logf(a1 + 1e-8f);
+            a0 = __logf(a0 + 1e-8f);   // MUFU.LG2 * ln 2, as in the log-mel epilogue (|error| ~1e-6)
+            a1 = __logf(a1 + 1e-8f);
         }
     }
     return make_float4(a0, a1, b0, b1);
