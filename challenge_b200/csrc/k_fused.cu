@@ -265,12 +265,15 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const int C = kFix ? 2 : p.C;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int FR = p.fr;
+    // fixed variants: 8 frames per tile and the 12 taps of the default mel shape, so that the
+    // shared-memory map folds into immediates
+    const int FR = kFix ? 8 : p.fr;
+    const int mel_taps = kFix ? (fixed_mel_L(0) + fixed_mel_L(1) + fixed_mel_L(2)) : p.mel_taps;
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
     uint64_t* empty = reinterpret_cast<uint64_t*>(sm + OFF_EMPTY);
     const int n_tiles = p.B * ((p.T + FR - 1) / FR) * p.n_pairs;
     const uint32_t slotB = slot_bytes(FR);
-    unsigned char* slots = sm + off_slots(p.mel_taps, FR);
+    unsigned char* slots = sm + off_slots(mel_taps, FR);
 
     // ---- one-time setup: tables, barriers, finite data in the stage buffers ----
     {
@@ -285,7 +288,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
             for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = i < p.n_mel ? p.mel_info[i] : 0u;
             float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
-            for (int i = tid; i < p.mel_taps * 32; i += blockDim.x) s_mw[i] = p.mel_w[i];
+            for (int i = tid; i < mel_taps * 32; i += blockDim.x) s_mw[i] = p.mel_w[i];
         }
         // rows of a slot outside a stage's frame range are read (and multiplied by 0) by the
         // frames the stage does not cover: they must hold finite numbers
@@ -380,7 +383,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         float w8[8];                               // Hann[n], n = lane + 32 i; Hann[n + 256] = 1 - Hann[n]
 #pragma unroll
         for (int i = 0; i < 8; ++i) w8[i] = p.hann[lane + 32 * i];
-        unsigned char* xch = sm + off_xch(p.mel_taps) + warp * kXwBytes;
+        unsigned char* xch = sm + off_xch(mel_taps) + warp * kXwBytes;
         const float4* s_tw1 = reinterpret_cast<const float4*>(sm + OFF_TW1) + lane;
         const unsigned char* my_rows = slots + j * 2048 + lane * 8;
         // running per-clip extrema of this lane (flushed when the clip changes)
@@ -664,7 +667,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         const int jt = lane & 7, half = (lane >> 3) & 1;
                         const int tt = (hdr.z & 0xffffff) + jt;
                         if (tt < p.T) {
-                            const unsigned char* x1 = sm + off_xch(p.mel_taps) + jt * kXwBytes + half * 8;
+                            const unsigned char* x1 = sm + off_xch(mel_taps) + jt * kXwBytes + half * 8;
                             const unsigned char* x0 = reinterpret_cast<const unsigned char*>(stg) + half * 8;
                             float* o = p.out + (size_t(b) * kBins * p.T + tt) * 8 + half * 4;
                             for (int f = warp * 2 + (lane >> 4); f < kBins; f += FR * 2) {
@@ -794,7 +797,7 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
             if (p.mel_f_lo + p.mel_f_n > 128) IRIS_LAUNCH(FM_MEL, 8, 0)
             else if (p.C != 2 || p.mel_L[0] != fixed_mel_L(0) || p.mel_L[1] != fixed_mel_L(1) ||
                      p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) || p.n_mel <= 64 ||
-                     !p.l2_hints || getenv("IRIS_NO_FIXED_EPI"))
+                     !p.l2_hints || FR != 8 || p.mel_taps != 12 || getenv("IRIS_NO_FIXED_EPI"))
                 IRIS_LAUNCH(FM_MEL, 4, 0)
             else if (p.do_minmax) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_MINMAX)
             else if (p.do_log) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_LOG)

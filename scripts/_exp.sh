@@ -1,2 +1,3 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python scripts/configs_bench.py 5 2>&1 | grep "configs\[2\]"
+echo "== fixed"; timeout 300 python scripts/kb_mel.py 2>&1 | tail -1
+echo "== generic"; IRIS_NO_FIXED_EPI=1 timeout 300 python scripts/kb_mel.py 2>&1 | tail -1
