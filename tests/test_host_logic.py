@@ -188,3 +188,29 @@ def test_dataset_lowering_recognises_the_sj_train_chain():
     ds = IrisDataset({}).map(D.augment).map(D.to_frame_labels).batch(2)
     fused, rest = ds._lower()
     assert fused['augment'] and not fused['frame_labels'] and len(rest) == 2
+
+
+def test_resample_len_matches_the_kaldi_port_without_a_gpu():
+    """iris_resample_len is host arithmetic (no device needed): it must agree with the oracle's
+    restatement of kaldi.py::_get_num_LR_output_samples for every rate pair / length."""
+    from challenge_b200 import _lib
+    from oracle.data_utils import _lr_num_output_samples
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for orig, new in ((44100, 16000), (48000, 16000), (8000, 16000), (22050, 16000), (11025, 16000),
+                      (32000, 16000), (16000, 16000), (96000, 16000), (16000, 8000)):
+        for n in [1, 2, 255, 256, 441, 16000, 44100, 160000] + [int(v) for v in rng.integers(1, 500000, 20)]:
+            assert lib.iris_resample_len(n, orig, new) == _lr_num_output_samples(n, orig, new), (orig, new, n)
+    assert lib.iris_resample_len(0, 44100, 16000) == 0
+
+
+def test_numa_binding_is_a_no_op_without_nvml():
+    """dist.bind_to_gpu_numa never raises: without a GPU / NVML it leaves the affinity alone."""
+    from challenge_b200.dist import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cores = bind_to_gpu_numa(0)
+    assert cores is None or set(cores) <= before
+    if cores is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
