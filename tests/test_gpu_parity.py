@@ -298,3 +298,71 @@ def test_full_size_properties_cfg2(engine, workload_factory):
     assert nmax_err(xn[clips], ref) < TOL
     assert np.array_equal(fr[clips], ref_y)
     assert np.array_equal(kp[clips], np.stack(ref_keep))
+
+
+def test_full_size_cfg3_four_channel_1024(engine, workload_factory):
+    """BASELINE config 3 at its full batch (1024 clips, 4 channels, magnitude + phase: 5.3 GB of
+    features): determinism, mask / label invariants on every clip, parity on a few clips."""
+    import torch
+    from challenge_b200 import _lib as L
+    w = workload_factory(4, seed=20203, n_bg=2, n_voice=16, n_noise=4)
+    B = 1024
+    d = _draw(w, B, 626, seed=3030)
+    engine.upload_plan(d)
+    frame, _, keep = engine.labels()
+    x = engine.features(L.FEAT_MAGPHASE)
+    assert tuple(x.shape) == (B, 257, 626, 8)
+    y = engine.features(L.FEAT_MAGPHASE)
+    assert torch.equal(x, y), 'not deterministic'
+    del y
+    assert bool(torch.isfinite(x).all())
+    assert bool((x[..., :4] >= 0).all())                                   # magnitudes
+    assert bool((x[..., 4:].abs() <= 3.1415928).all())                      # phases in [-pi, pi]
+    for b in range(0, B, 97):                                               # masked cells: |.| == 0 exactly
+        for size, off in d.time_masks[b]:
+            assert bool((x[b, :, off:off + size, :4] == 0).all())
+        for size, off in d.freq_masks[b]:
+            assert bool((x[b, off:off + size, :, :4] == 0).all())
+    fr = frame.cpu().numpy()
+    kp = keep.cpu().numpy()
+    assert set(np.unique(fr)) <= {0.0, 1.0} and np.all(kp[:, 0] == 1)
+    clips = [0, 511, 1023]
+    ref, ref_y, _, ref_keep = _oracle(w, d, mode='magphase', clips=clips)
+    got = x[clips].cpu().numpy()
+    assert nmax_err(got[..., :4], ref[..., :4]) < TOL
+    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    assert np.array_equal(fr[clips], ref_y)
+    assert np.array_equal(kp[clips], np.stack(ref_keep))
+
+
+def test_full_size_cfg4_shards_equal_the_whole_batch(engine, workload_factory):
+    """BASELINE config 4 (batch 8192 sharded over 8 GPUs): every rank receives a contiguous slice of
+    the host plan.  Run here on one GPU: the 8 slices of 1024 clips must reproduce
+    the whole-batch launch bit for bit -- features, labels, keep flags -- and their metric counts
+    must add up to the whole batch's (what the NCCL sum all-reduce computes)."""
+    import torch
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    B, G = 8192, 8
+    d = _draw(w, B, 626, seed=4040)
+    engine.upload_plan(d)
+    frame, _, keep = engine.labels()
+    x = engine.features(L.FEAT_LOGMEL_MINMAX)
+    yp = torch.clamp(frame + 0.35 * torch.randn(frame.shape, device=frame.device,
+                                                generator=torch.Generator(frame.device).manual_seed(5)), 0, 1)
+    triples, tpfpfn, _ = engine.metric_counts(frame, yp)
+    total = torch.zeros(3, dtype=torch.int64, device=frame.device)
+    for r in range(G):
+        lo, hi = r * B // G, (r + 1) * B // G
+        engine.upload_plan(d.slice(lo, hi))
+        f_r, _, k_r = engine.labels()
+        x_r = engine.features(L.FEAT_LOGMEL_MINMAX)
+        assert torch.equal(x_r, x[lo:hi]), r
+        assert torch.equal(f_r, frame[lo:hi]) and torch.equal(k_r, keep[lo:hi]), r
+        t_r, c_r, _ = engine.metric_counts(f_r, yp[lo:hi])
+        assert torch.equal(t_r, triples[lo:hi]), r
+        total += c_r
+    assert torch.equal(total, tpfpfn)
+    xn = x[::1024].cpu().numpy()                       # every clip spans [log 1e-8, log(1 + 1e-8)]
+    assert np.allclose(xn.reshape(len(xn), -1).min(1), np.log(np.float32(1e-8)), rtol=0, atol=1e-5)
+    assert np.allclose(xn.reshape(len(xn), -1).max(1), 0, atol=1e-6)
