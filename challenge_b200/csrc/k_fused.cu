@@ -1,4 +1,4 @@
-// Fused hot path (v5): gather + time-domain mix of the gained source frames, window,
+// Fused hot path: gather + time-domain mix of the gained source frames, window,
 // 512-point FFT per frame (two real channels packed into one complex transform, ONE WARP per
 // frame, 16 points per lane), then the epilogue (SpecAugment masks, channel remap,
 // stft_filter, complex / mag-phase / log-mag-phase output, or magnitude -> sparse mel ->
