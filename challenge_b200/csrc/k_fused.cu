@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
     const int tpc = (p.T + FR - 1) / FR;
     const int per_clip = tpc * p.n_pairs;
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    // programmatic dependent launch: k_fused may start its prologue (tables, barriers, zero fill of
+    // the stage buffers) now; it waits for this grid before it touches a tile block
+    cudaTriggerProgrammaticLaunchCompletion();
     if (tile >= p.B * per_clip) return;
     if (tile < p.B && p.minmax != nullptr) {   // per-clip extrema scratch of the launch that follows
         p.minmax[2 * tile] = 0u;
@@ -304,6 +307,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         fence_proxy_async();   // the zero fill (generic proxy) precedes the bulk copies (async proxy)
         __syncthreads();
     }
+    // everything above overlapped k_tiles (programmatic dependent launch); its tile blocks and the
+    // zeroed extrema scratch are visible from here on
+    cudaGridDependencySynchronize();
 
     if (warp == FR) {
         // =========================== producer warp ===========================
@@ -358,6 +364,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 }
             }
         }
+        // no work left to claim: a kernel launched behind this one with programmatic stream
+        // serialization (k_logmel_post) may be scheduled; it still waits for the whole grid
+        cudaTriggerProgrammaticLaunchCompletion();
         // end marker: a TileBlock with n == 0 behind one more (empty) stage
         {
             unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
@@ -753,6 +762,7 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
     const int threads = (FR + 1) * 32;
+    const int pdl = getenv("IRIS_NO_PDL") ? 0 : 1;
     int dev = 0;
     cudaGetDevice(&dev);
     // persistent grid: as many CTAs as are resident at once, asked of the occupancy calculator once
@@ -787,7 +797,18 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
         }                                                                                       \
         const long long max_ctas = (long long)num_sms * per_sm;                                 \
         const int grid = int(n_tiles < max_ctas ? n_tiles : max_ctas);                          \
-        k_fused<M, NJV, EPIV><<<grid, threads, smem, stream>>>(p);                                    \
+        cudaLaunchConfig_t cfg{};                                                               \
+        cfg.gridDim = dim3(unsigned(grid));                                                     \
+        cfg.blockDim = dim3(unsigned(threads));                                                 \
+        cfg.dynamicSmemBytes = smem;                                                            \
+        cfg.stream = stream;                                                                    \
+        cudaLaunchAttribute attr[1];                                                            \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                        \
+        attr[0].val.programmaticStreamSerializationAllowed = pdl;                               \
+        cfg.attrs = attr;                                                                       \
+        cfg.numAttrs = 1;                                                                       \
+        cudaError_t le = cudaLaunchKernelEx(&cfg, k_fused<M, NJV, EPIV>, p);                    \
+        if (le != cudaSuccess) return le;                                                       \
     }
     switch (mode) {
         case FM_COMPLEX: IRIS_LAUNCH(FM_COMPLEX, 8, 0) break;

@@ -7,6 +7,8 @@
 //   y = log((x - min) / max(max - min, 1e-8) + 1e-8)
 // is evaluated as log2((x - min) * inv + 1e-8) * ln2 with inv = 1 / max(max - min, 1e-8):
 // FADD, FFMA, MUFU.LG2, FMUL per element.
+#include <cstdlib>
+
 #include "iris_common.cuh"
 #include "iris_launch.h"
 
@@ -25,6 +27,7 @@ __global__ void __launch_bounds__(kPostThreads) k_logmel_post(float* __restrict_
                                                               size_t per_clip, int do_minmax,
                                                               int do_log, unsigned* done) {
     const int b = blockIdx.y;
+    cudaGridDependencySynchronize();   // launched behind k_fused with programmatic stream serialization
     float inv = 1.f, mn = 0.f;
     const float eps = do_log ? 1e-8f : 0.f;
     if (do_minmax) {
@@ -77,9 +80,20 @@ cudaError_t launch_logmel_post(float* x, uint32_t* minmax, int B, size_t per_cli
     for (int b0 = 0; b0 < B; b0 += 65535) {
         int nb = B - b0 < 65535 ? B - b0 : 65535;
         dim3 grid(kPostChunks, nb);
-        k_logmel_post<<<grid, kPostThreads, 0, stream>>>(
-            x + size_t(b0) * per_clip, minmax ? minmax + 2 * size_t(b0) : nullptr, per_clip, do_minmax,
-            do_log, minmax ? minmax + 2 * size_t(B) + b0 : nullptr);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kPostThreads);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = getenv("IRIS_NO_PDL") ? 0 : 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_logmel_post, x + size_t(b0) * per_clip,
+                                           minmax ? minmax + 2 * size_t(b0) : static_cast<uint32_t*>(nullptr), per_clip,
+                                           do_minmax, do_log,
+                                           minmax ? minmax + 2 * size_t(B) + b0 : static_cast<unsigned*>(nullptr));
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
