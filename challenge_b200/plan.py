@@ -88,6 +88,16 @@ def placement(n_frame, padded_len, ratio):
     return 0, int(padded_len)
 
 
+def _randint(rng, high, size=None):
+    """Uniform integers in ``[0, high)`` for an ARRAY of exclusive upper bounds: ``floor(u * high)``
+    with ``u`` a float64 in [0, 1) (never reaches ``high``; the bias is below 2**-30 for the frame
+    and bin counts drawn here).  ``Generator.integers`` with array bounds is ~3x slower, and the
+    host draws are what bounds the pipeline once the features stay on the device."""
+    high = np.asarray(high)
+    u = rng.random(high.shape if size is None else size)
+    return (u * high).astype(np.int64)
+
+
 def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=None,
                max_voices=0, max_noises=0, snr=-20, min_ratio=2 / 3, min_noise_ratio=1 / 2,
                n_time_masks=0, time_mask_max=24, n_freq_masks=0, freq_mask_max=16,
@@ -112,7 +122,7 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
                    min_ratio=min_ratio, min_noise_ratio=min_noise_ratio)
     bgT = bg_frames[d.bg_id].astype(np.int64)
     tiled = bgT * ((T + bgT - 1) // bgT)
-    d.bg_offset = rng.integers(0, tiled - T + 1).astype(np.int32)         # random_crop (35)
+    d.bg_offset = _randint(rng, tiled - T + 1).astype(np.int32)           # random_crop (35)
     if V > 0:
         voice_frames = np.asarray(voice_frames)
         d.voice_id = ids('voice', len(voice_frames), B * V).reshape(B, V)
@@ -127,7 +137,7 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
                 'n_frame=%d (pipeline.py:68-69)' % (b, int(vP[b]), T))
         live = np.arange(V)[None, :] < d.n_voices[:, None]
         d.voice_u = (rng.random((B, V), dtype=f32) * f32(-snr / 10)) * live          # (50)
-        d.voice_offset = (rng.integers(0, (length - T)[:, None], size=(B, V)) * live  # (69)
+        d.voice_offset = (_randint(rng, (length - T)[:, None], size=(B, V)) * live  # (69)
                           ).astype(np.int32)
         d.voice_gain = np.power(f32(10.), -d.voice_u, dtype=f32)           # pow(10., -u)
     if M > 0:
@@ -141,16 +151,16 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
             raise InvalidArgumentError('noise group shorter than n_frame after padding')
         live = np.arange(M)[None, :] < d.n_noises[:, None]
         d.noise_u = (rng.random((B, M), dtype=f32) * f32(2)) * live        # (94)
-        d.noise_offset = (rng.integers(0, (length - T + 1)[:, None], size=(B, M)) * live  # (103)
+        d.noise_offset = (_randint(rng, (length - T + 1)[:, None], size=(B, M)) * live  # (103)
                           ).astype(np.int32)
         d.noise_gain = np.power(f32(10.), -d.noise_u, dtype=f32)
     if n_time_masks:                                                       # transforms.py:25-26
         size = rng.integers(0, time_mask_max, size=(B, n_time_masks))
-        off = rng.integers(0, T - size)
+        off = _randint(rng, T - size)
         d.time_masks = np.stack([size, off], -1).astype(np.int32)
     if n_freq_masks:
         size = rng.integers(0, freq_mask_max, size=(B, n_freq_masks))
-        off = rng.integers(0, n_bins - size)
+        off = _randint(rng, n_bins - size)
         d.freq_masks = np.stack([size, off], -1).astype(np.int32)
     if merge_extra:                                                        # data_utils.py:109
         d.merge_factor = f32(0.1) + rng.random((B, merge_extra), dtype=f32) * f32(0.8)
