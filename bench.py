@@ -34,8 +34,8 @@ CFG = dict(n_chan=2, batch=256, n_frame=626, max_voices=7, max_noises=2, snr=-20
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused<FM_MEL> launch of this workload,
 # from the committed ncu --set full capture (profiles/); below the algorithmic bytes because the
 # 175 MB of banks are shared by the 256 clips and partly stay in the 126 MB L2
-NCU_TRAFFIC_BYTES = 470943488
-NCU_TRAFFIC_SRC = 'profiles/r01_v9_fused_ncu_raw.txt (441.4 MB read + 29.6 MB written; the mel rows stay in L2 for k_logmel_post)'
+NCU_TRAFFIC_BYTES = 439142144
+NCU_TRAFFIC_SRC = 'profiles/r01_v10_fused_ncu_raw.txt (411.4 MB read + 27.8 MB written; the mel rows stay in L2 for k_logmel_post)'
 METRIC = 'augmented spectrogram clips/sec'
 UNIT = 'clips/s'
 
