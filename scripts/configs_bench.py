@@ -37,20 +37,20 @@ def banks(C, seed):
     return bf, vf, nf
 
 rows = []
-def run(name, C, B, mode, aug, seed, metrics=False):
+def run(name, C, B, mode, aug, seed, metrics=False, T=626):
     bf, vf, nf = banks(C, seed)
     rng = np.random.default_rng(seed)
     if aug:
-        d = draw_batch(rng, B, 626, bf, vf, nf, max_voices=7, max_noises=2, snr=-20, min_ratio=1, n_time_masks=6, n_freq_masks=1)
+        d = draw_batch(rng, B, T, bf, vf, nf, max_voices=7, max_noises=2, snr=-20, min_ratio=1, n_time_masks=6, n_freq_masks=1)
     else:
-        d = draw_batch(rng, B, 626, bf)
+        d = draw_batch(rng, B, T, bf)
     eng.upload_plan(d)
     keep = None
     if aug:
         _, _, keep = eng.labels(); keep = keep.cpu().numpy()
     out = torch.empty(eng.feature_shape(mode), device='cuda')
     bi, bo = eng.plan_bytes(mode, keep)
-    y_pred = torch.rand((B, 626, 3), device='cuda') if metrics else None
+    y_pred = torch.rand((B, T, 3), device='cuda') if metrics else None
     def step():
         frame = None
         if aug:
@@ -69,6 +69,8 @@ def run(name, C, B, mode, aug, seed, metrics=False):
 
 run('configs[0] 2-ch, no augmentation -> min-max log-mel', 2, 32, L.FEAT_LOGMEL_MINMAX, False, 20200)
 us1 = run('configs[1] 2-ch mix + masks -> min-max log-mel + labels + counts', 2, 256, L.FEAT_LOGMEL_MINMAX, True, 20201, metrics=True)
+run('configs[0] at the trainers\' default n_frame = 512 (sj_train.py:59)', 2, 32, L.FEAT_LOGMEL_MINMAX, False, 20200, T=512)
+run('configs[1] at the trainers\' default n_frame = 512 (sj_train.py:59)', 2, 256, L.FEAT_LOGMEL_MINMAX, True, 20201, metrics=True, T=512)
 run('configs[2] 4-ch mix + masks -> magnitude + phase + labels', 4, 1024, L.FEAT_MAGPHASE, True, 20202)
 run('configs[2] 4-ch mix + masks -> log-magnitude + phase + labels', 4, 1024, L.FEAT_LOG_MAGPHASE, True, 20202)
 run('configs[3] shard of 8 GPUs (8192 / 8) -> min-max log-mel + labels + counts', 2, 1024, L.FEAT_LOGMEL_MINMAX, True, 20203, metrics=True)
