@@ -19,8 +19,6 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
     float* L = reinterpret_cast<float*>(s_raw);                       // [T*K]
     float* lab = L + TK;                                               // [V*K]
     uint8_t* act = reinterpret_cast<uint8_t*>(lab + p.V * p.K);       // [V][T]
-    __shared__ float s_max[32];
-    __shared__ int s_keep;
     const int nv = p.n_voices[b];
     for (int i = threadIdx.x; i < TK; i += blockDim.x) L[i] = 0.f;
     // per-voice metadata first (one round trip for ids / shifts, one for the frame counts), then
@@ -62,23 +60,17 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
         }
         const uint8_t* av = act + v * p.T;
         const float* lb = lab + v * p.K;
-        // max over (t, c) of (sum of accepted labels + candidate)   (pipeline.py:78)
-        float mx = 0.f;
+        // no_overlap = max over (t, c) of (sum of accepted labels + candidate) < 2  (pipeline.py:78-79)
+        //            = no element reaches 2: one block-wide OR instead of a max reduction.  Thread
+        // x owns frames x, x + blockDim, ... for every voice, so L needs no barrier of its own.
+        int hit = 0;
         for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
             const float a = av[t] ? 1.f : 0.f;
-            for (int c = 0; c < p.K; ++c) mx = fmaxf(mx, L[t * p.K + c] + lb[c] * a);
+            for (int c = 0; c < p.K; ++c) hit |= (L[t * p.K + c] + lb[c] * a >= 2.f);
         }
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float m = s_max[0];
-            for (int w = 1; w < int(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
-            s_keep = (m < 2.f) ? 1 : 0;                       // no_overlap (pipeline.py:78-79)
-            p.keep[size_t(b) * p.V + v] = uint8_t(s_keep);
-        }
-        __syncthreads();
-        const float keep = s_keep ? 1.f : 0.f;
+        const int keep_i = __syncthreads_or(hit) ? 0 : 1;
+        if (threadIdx.x == 0) p.keep[size_t(b) * p.V + v] = uint8_t(keep_i);
+        const float keep = keep_i ? 1.f : 0.f;
         for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
             const float a = av[t] ? 1.f : 0.f;
             for (int c = 0; c < p.K; ++c) {
@@ -87,8 +79,8 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
                 if (lv) lv[t * p.K + c] = cand;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();   // the final copy below walks L with another thread-to-element map
     float* out = p.frame_labels + size_t(b) * TK;
     for (int i = threadIdx.x; i < TK; i += blockDim.x) out[i] = L[i];
 }
