@@ -106,6 +106,7 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
     lp.n_voices = c->d_n_voices;
     lp.voice_id = c->d_voice_id;
     lp.voice_shift = c->d_voice_shift;
+    lp.voice_kt = c->d_voice_kt;
     lp.n_frames = vb.d_n_frames.as<int32_t>();
     lp.activity = vb.activity.as<uint8_t>();
     lp.act_stride = vb.max_frames;
@@ -586,6 +587,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     c->h_seg_len.clear();
     c->h_seg_ptr.assign(B + 1, 0);
     std::vector<int32_t> vshift(size_t(B) * (V > 0 ? V : 1), 0);
+    std::vector<int32_t> vkt(size_t(B) * (V > 0 ? V : 1), 0);   // frames of the voice; 0 behind n_voices
     auto push = [&](const Bank& bank, int id, int shift, int lo, int hi, float gain, int keep_idx) {
         if (lo >= hi) return;
         Seg s;
@@ -657,6 +659,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
                 const int shift = off - s0;
                 vshift[size_t(b) * V + v] = shift;
                 const int kT = vb.n_frames[vid];
+                vkt[size_t(b) * V + v] = kT;
                 push(vb, vid, shift, std::max(0, -shift), std::min(T, kT - shift),
                      pl->voice_gain[size_t(b) * V + v], b * V + v);
             }
@@ -718,6 +721,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     const size_t o_nv = o;   o = align_up(o + size_t(B) * 4, 16);
     const size_t o_vid = o;  o = align_up(o + size_t(B) * std::max(V, 1) * 4, 16);
     const size_t o_vsh = o;  o = align_up(o + size_t(B) * std::max(V, 1) * 4, 16);
+    const size_t o_vkt = o;  o = align_up(o + size_t(B) * std::max(V, 1) * 4, 16);
     const size_t o_tm = o;   o = align_up(o + size_t(B) * n_tm * 8, 16);
     const size_t o_fm = o;   o = align_up(o + size_t(B) * n_fm * 8, 16);
     const size_t o_mf = o;   o = align_up(o + size_t(B) * n_extra * 4, 16);
@@ -735,6 +739,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         for (int b = 0; b < B; ++b) nv[b] = (V == 1) ? 1 : pl->n_voices[b];
         memcpy(h + o_vid, pl->voice_id, size_t(B) * V * 4);
         memcpy(h + o_vsh, vshift.data(), size_t(B) * V * 4);
+        memcpy(h + o_vkt, vkt.data(), size_t(B) * V * 4);
     }
     if (n_tm) memcpy(h + o_tm, pl->time_masks, size_t(B) * n_tm * 8);
     if (n_fm) memcpy(h + o_fm, pl->freq_masks, size_t(B) * n_fm * 8);
@@ -751,6 +756,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     c->d_n_voices = reinterpret_cast<int32_t*>(d + o_nv);
     c->d_voice_id = reinterpret_cast<int32_t*>(d + o_vid);
     c->d_voice_shift = reinterpret_cast<int32_t*>(d + o_vsh);
+    c->d_voice_kt = reinterpret_cast<int32_t*>(d + o_vkt);
     c->d_tmask = n_tm ? reinterpret_cast<int32_t*>(d + o_tm) : nullptr;
     c->d_fmask = n_fm ? reinterpret_cast<int32_t*>(d + o_fm) : nullptr;
     c->d_merge_f = n_extra ? reinterpret_cast<float*>(d + o_mf) : nullptr;

@@ -95,7 +95,7 @@ struct iris_ctx {
     // device views into plan_blob
     Seg* d_segs = nullptr;
     int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
-            *d_voice_shift = nullptr, *d_tmask = nullptr, *d_fmask = nullptr;
+            *d_voice_shift = nullptr, *d_voice_kt = nullptr, *d_tmask = nullptr, *d_fmask = nullptr;
     float *d_merge_f = nullptr, *d_merge_sf = nullptr;
     // roofline measurement hook
     bool profile = false;

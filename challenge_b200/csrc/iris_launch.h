@@ -32,6 +32,7 @@ struct LabelParams {
     const int32_t* n_voices;     // [B]
     const int32_t* voice_id;     // [B,V]
     const int32_t* voice_shift;  // [B,V]  source frame k = t + shift
+    const int32_t* voice_kt;     // [B,V]  frames of the voice (0 behind n_voices): n_frames[voice_id], resolved on the host
     const int32_t* n_frames;     // [n_items] true frame count of each voice
     const uint8_t* activity;     // [n_items, act_stride]
     int act_stride;

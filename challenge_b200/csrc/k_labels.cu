@@ -21,18 +21,15 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
     uint8_t* act = reinterpret_cast<uint8_t*>(lab + p.V * p.K);       // [V][T]
     const int nv = p.n_voices[b];
     for (int i = threadIdx.x; i < TK; i += blockDim.x) L[i] = 0.f;
-    // per-voice metadata first (one round trip for ids / shifts, one for the frame counts), then
+    // per-voice metadata first (ids / shifts / frame counts: one round trip), then
     // ONE flattened gather of all V x T activity bytes: the loads are independent, so they
     // pipeline instead of paying a memory round trip per voice
     __shared__ int s_id[64], s_shift[64], s_kT[64];
     for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
-        int id = 0, shift = 0, kT = 0;
-        if (v < nv) {
-            id = p.voice_id[size_t(b) * p.V + v];
-            shift = p.voice_shift[size_t(b) * p.V + v];
-            kT = p.n_frames[id];
-        }
-        s_id[v] = id; s_shift[v] = shift; s_kT[v] = kT;
+        // one round trip: the frame count of the voice comes with the plan (0 behind n_voices)
+        s_id[v] = p.voice_id[size_t(b) * p.V + v];
+        s_shift[v] = p.voice_shift[size_t(b) * p.V + v];
+        s_kT[v] = p.voice_kt[size_t(b) * p.V + v];
     }
     __syncthreads();
     {
