@@ -214,3 +214,22 @@ def test_numa_binding_is_a_no_op_without_nvml():
         assert os.sched_getaffinity(0) == before
     else:
         os.sched_setaffinity(0, before)
+
+
+def test_default_mel_matrix_has_the_shape_the_fixed_kernel_instances_assume():
+    """k_fused<FM_MEL, 4, EPI_C2 | ...> unrolls the projection for filters of at most 2 / 4 / 6 bins
+    in the three rounds of 32 and bins below 128 (fixed_mel_L in k_fused.cu; the launcher checks the
+    same and falls back to the generic instance otherwise).  The reference's matrix
+    (transforms.py:55, linear_to_mel_weight_matrix(80, 257, 16000)) has exactly that shape."""
+    from oracle.transforms import linear_to_mel_weight_matrix
+    W = linear_to_mel_weight_matrix(80, 257, 16000)
+    lens, hi = [], 0
+    for m in range(80):
+        nz = np.nonzero(W[:, m])[0]
+        assert np.all(np.diff(nz) == 1)                      # contiguous support
+        lens.append(len(nz))
+        hi = max(hi, int(nz[-1]))
+    rounds = [max(lens[32 * r:32 * r + 32]) for r in range(3)]
+    assert [n + (n & 1) for n in rounds] == [2, 4, 6] and hi < 128
+    src = open(os.path.join(ROOT, 'challenge_b200', 'csrc', 'k_fused.cu')).read()
+    assert 'return r == 0 ? 2 : (r == 1 ? 4 : (r == 2 ? 6 : 0));' in src
