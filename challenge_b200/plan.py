@@ -115,7 +115,7 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
     def ids(name, n, k):
         if name in streams:
             return streams[name].take(k)
-        return rng.integers(0, n, size=k).astype(np.int32)
+        return rng.integers(0, n, size=k, dtype=np.int32)
 
     d = BatchDraws(batch=B, n_frame=T, max_voices=V, max_noises=M,
                    bg_id=ids('bg', len(bg_frames), B), bg_offset=None,
@@ -126,7 +126,8 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
     if V > 0:
         voice_frames = np.asarray(voice_frames)
         d.voice_id = ids('voice', len(voice_frames), B * V).reshape(B, V)
-        d.n_voices = (rng.integers(1, V, size=B) if V > 1 else np.ones(B)).astype(np.int32)  # (43)
+        d.n_voices = (rng.integers(1, V, size=B, dtype=np.int32) if V > 1
+                      else np.ones(B, np.int32))                           # (43)
         vP = voice_frames[d.voice_id].max(axis=1)                          # padded_batch (155)
         pad = T - (f32(min_ratio) * vP.astype(f32)).astype(np.int32)       # (58-59)
         length = np.where(pad > 0, vP + 2 * pad, vP)
@@ -143,7 +144,7 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
     if M > 0:
         noise_frames = np.asarray(noise_frames)
         d.noise_id = ids('noise', len(noise_frames), B * M).reshape(B, M)
-        d.n_noises = rng.integers(0, M, size=B).astype(np.int32)          # (87)
+        d.n_noises = rng.integers(0, M, size=B, dtype=np.int32)           # (87)
         nP = noise_frames[d.noise_id].max(axis=1)
         pad = T - (f32(min_noise_ratio) * nP.astype(f32)).astype(np.int32)  # (95-96)
         length = np.where(pad > 0, nP + 2 * pad, nP)
@@ -155,13 +156,15 @@ def draw_batch(rng, batch, n_frame, bg_frames, voice_frames=None, noise_frames=N
                           ).astype(np.int32)
         d.noise_gain = np.power(f32(10.), -d.noise_u, dtype=f32)
     if n_time_masks:                                                       # transforms.py:25-26
-        size = rng.integers(0, time_mask_max, size=(B, n_time_masks))
-        off = _randint(rng, T - size)
-        d.time_masks = np.stack([size, off], -1).astype(np.int32)
+        tm = np.empty((B, n_time_masks, 2), np.int32)
+        tm[..., 0] = rng.integers(0, time_mask_max, size=(B, n_time_masks), dtype=np.int32)
+        tm[..., 1] = _randint(rng, T - tm[..., 0])
+        d.time_masks = tm
     if n_freq_masks:
-        size = rng.integers(0, freq_mask_max, size=(B, n_freq_masks))
-        off = _randint(rng, n_bins - size)
-        d.freq_masks = np.stack([size, off], -1).astype(np.int32)
+        fm = np.empty((B, n_freq_masks, 2), np.int32)
+        fm[..., 0] = rng.integers(0, freq_mask_max, size=(B, n_freq_masks), dtype=np.int32)
+        fm[..., 1] = _randint(rng, n_bins - fm[..., 0])
+        d.freq_masks = fm
     if merge_extra:                                                        # data_utils.py:109
         d.merge_factor = f32(0.1) + rng.random((B, merge_extra), dtype=f32) * f32(0.8)
     return d
