@@ -23,6 +23,15 @@ import sys
 import threading
 import time
 
+# The CPU arm runs one process per core: BLAS / OpenMP pools inside each worker would
+# oversubscribe the box (round 1: 82 clips/s on 16 cores, ~500 with one thread per worker).
+# numpy reads these when it is first imported, so they are set before that; the GPU arm only
+# uses numpy for the host draws.
+_THREAD_ENV = ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS',
+               'VECLIB_MAXIMUM_THREADS')
+for _k in _THREAD_ENV:
+    os.environ[_k] = '1'
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

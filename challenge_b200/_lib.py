@@ -33,6 +33,40 @@ class IrisPlan(C.Structure):
     ]
 
 
+class IrisDrawConfig(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('n_frame', C.c_int32), ('max_voices', C.c_int32), ('max_noises', C.c_int32),
+        ('min_ratio', C.c_float), ('min_noise_ratio', C.c_float), ('snr', C.c_float),
+        ('n_time_masks', C.c_int32), ('time_mask_max', C.c_int32), ('n_freq_masks', C.c_int32),
+        ('freq_mask_max', C.c_int32), ('n_bins', C.c_int32), ('merge_extra', C.c_int32),
+    ]
+
+
+class IrisDraws(C.Structure):
+    _fields_ = [
+        ('bg_id', _i32p), ('bg_offset', _i32p),
+        ('n_voices', _i32p), ('voice_id', _i32p), ('voice_u', _f32p), ('voice_gain', _f32p), ('voice_offset', _i32p),
+        ('n_noises', _i32p), ('noise_id', _i32p), ('noise_u', _f32p), ('noise_gain', _f32p), ('noise_offset', _i32p),
+        ('time_masks', _i32p), ('freq_masks', _i32p), ('merge_factor', _f32p),
+    ]
+
+
+class IrisStepConfig(C.Structure):
+    _fields_ = [('draw', IrisDrawConfig), ('stft_filter', C.c_int32), ('chan_remap', C.c_int32),
+                ('n_out_chan', C.c_int32), ('feature_mode', C.c_int32)]
+
+
+class IrisStepIO(C.Structure):
+    _fields_ = [
+        ('uniforms', C.c_void_p), ('streams', C.POINTER(C.c_void_p)),
+        ('d_features', C.c_void_p), ('d_frame_labels', C.c_void_p), ('d_labels_vtk', C.c_void_p),
+        ('d_keep', C.c_void_p),
+        ('d_y_pred', C.c_void_p), ('threshold', C.c_float), ('d_triples', C.c_void_p),
+        ('d_counts', C.c_void_p), ('comm', C.c_void_p), ('d_counts_reduced', C.c_void_p),
+        ('d_triples_send', C.c_void_p), ('d_triples_global', C.c_void_p), ('global_batch', C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols include/iris.h declares
 SIGNATURES = {
     'iris_abi_version': (C.c_int, []),
@@ -102,6 +136,31 @@ SIGNATURES = {
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'iris_op_get_er': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    # one call per batch, host planner, NCCL, pinned memory, DLPack (include/iris.h, round 2)
+    'iris_shuffle_create': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    'iris_shuffle_destroy': (C.c_int, [C.c_void_p]),
+    'iris_shuffle_take': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'iris_draw_uniforms_per_clip': (C.c_int, [C.POINTER(IrisDrawConfig)]),
+    'iris_draw_batch': (C.c_int, [C.POINTER(IrisDrawConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                  C.POINTER(IrisDraws)]),
+    'iris_step': (C.c_int, [C.c_void_p, C.POINTER(IrisStepConfig), C.POINTER(IrisStepIO), C.c_void_p]),
+    'iris_counts_wait': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'iris_step_draws': (C.c_int, [C.c_void_p, C.POINTER(IrisDraws)]),
+    'iris_allreduce_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_void_p]),
+    'iris_nccl_unique_id': (C.c_int, [C.c_void_p]),
+    'iris_nccl_comm_create': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    'iris_nccl_comm_destroy': (C.c_int, [C.c_void_p]),
+    'iris_er_from_triples': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'iris_host_alloc': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    'iris_host_free': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    'iris_features_dlpack': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'iris_labels_dlpack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'iris_step_dlpack': (C.c_int, [C.c_void_p, C.POINTER(IrisStepConfig), C.c_void_p, C.POINTER(C.c_void_p),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    'iris_mel_fusable': (C.c_int, [C.c_void_p]),
+    'iris_max_segments': (C.c_int, []),
 }
 PW_C2MP, PW_MP2C, PW_LOG_MAGPHASE, PW_LOG_ON_MEL, PW_MULTIPLY = range(5)
 MAP_MONO_CHAN, MAP_STEREO_MONO, MAP_MERGE_AUG = range(3)
@@ -125,6 +184,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def dlpack_pointer(capsule):
+    """``DLManagedTensor*`` behind a DLPack PyCapsule (name "dltensor": not consumed yet)."""
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    return C.c_void_p(C.pythonapi.PyCapsule_GetPointer(capsule, b'dltensor'))
 
 
 def check(rc):

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libiris.so')
 SOURCES = ['iris_abi.cu', 'k_fused.cu', 'k_post.cu', 'k_bank.cu', 'k_labels.cu', 'k_metrics.cu',
-           'k_ops.cu', 'k_eval.cu', 'k_spec.cu', 'k_resample.cu', 'iris_ops_abi.cu']
+           'k_ops.cu', 'k_eval.cu', 'k_spec.cu', 'k_resample.cu', 'iris_ops_abi.cu', 'iris_step.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
 
@@ -46,7 +46,7 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, obj_dir=None):
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         if not os.path.exists(s):
-            continue
+            raise RuntimeError('listed CUDA source %s is missing' % s)
         o = os.path.join(OBJ, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _stale(o, [s] + headers):
@@ -57,7 +57,7 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, obj_dir=None):
             if r.returncode:
                 raise RuntimeError('nvcc failed on %s' % src)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

@@ -76,14 +76,14 @@ void set_geometry(iris_ctx* c, FusedParams& p, int n_chan, bool mel) {
     (void)c;
 }
 
-int ensure_stage(iris_ctx* c, size_t bytes) {
-    if (bytes <= c->h_stage_cap) return IRIS_OK;
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->h_stage = nullptr;
-    c->h_stage_cap = 0;
+int ensure_stage(iris_ctx* c, int slot, size_t bytes) {
+    if (bytes <= c->h_stage_cap[slot]) return IRIS_OK;
+    if (c->h_stage[slot]) cudaFreeHost(c->h_stage[slot]);
+    c->h_stage[slot] = nullptr;
+    c->h_stage_cap[slot] = 0;
     const size_t want = bytes + bytes / 4 + 4096;
-    CU(cudaMallocHost(&c->h_stage, want));
-    c->h_stage_cap = want;
+    CU(cudaMallocHost(&c->h_stage[slot], want));
+    c->h_stage_cap[slot] = want;
     return IRIS_OK;
 }
 
@@ -254,10 +254,11 @@ int iris_ctx_create(int device, iris_ctx** out) {
         return fail(IRIS_ERR_UNSUPPORTED, "libiris is built for sm_100a (Blackwell B200) only");
     }
     c->num_sms = prop.multiProcessorCount;
-    if ((e = cudaEventCreateWithFlags(&c->stage_free, cudaEventDisableTiming)) != cudaSuccess) {
-        delete c;
-        return cuda_fail(e, "cudaEventCreate");
-    }
+    for (int i = 0; i < iris_ctx::kStageRing; ++i)
+        if ((e = cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) {
+            delete c;
+            return cuda_fail(e, "cudaEventCreate");
+        }
     int rc = build_tables(c);
     if (rc != IRIS_OK) {
         delete c;
@@ -278,8 +279,11 @@ int iris_ctx_destroy(iris_ctx* c) {
                       &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->ts, &c->sched,
                       &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops, &c->eval_scratch, &c->spec_scratch})
         d->release();
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->stage_free) cudaEventDestroy(c->stage_free);
+    for (int i = 0; i < iris_ctx::kStageRing; ++i) {
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+    }
+    iris_step_release(c);
     for (auto& ev : c->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete c;
     return IRIS_OK;
@@ -338,18 +342,106 @@ int iris_set_mel(iris_ctx* c, int n_mel, int n_bins, const float* w) {
     for (int r = 0; r < 4; ++r) wide = wide || L[r] > fused_max_mel_filter();
     c->mel_fusable = taps <= fused_max_mel_taps() && !odd && !wide;
     if (!c->mel_fusable) return IRIS_OK;   // iris_features(mel modes) then reports UNSUPPORTED
-    std::vector<uint32_t> info(n_mel, 0);
+    // ---- filter -> (round, lane) assignment ----
+    // Lane l of round r projects filter slot[r][l] (or nothing).  Any assignment gives the same
+    // numbers (every lane stores its own mel row); what it changes is the bank-conflict count of
+    // the magnitude reads: the 16 lanes of a half-warp read (|ch0|, |ch1|) pairs (8 bytes) at
+    // bins start + q, which is conflict-free iff their starts are distinct modulo 16 (or equal).
+    // In natural order (filter m = lane + 32 r) the TF matrix costs 44 shared-memory wavefronts
+    // per frame for its 12 taps; the search below brings it to ~30 (24 = no conflict at all).
+    // Cost of a round = trip count x (wavefronts of half-warp 0 + half-warp 1); the sum of the
+    // trip counts may not grow.  Deterministic annealing over slot swaps (LCG, fixed seed).
+    const int n_slots = 128;
+    std::vector<int> slot(n_slots, -1);
+    for (int m = 0; m < n_mel; ++m) slot[m] = lo_of[m] < 0 ? -1 : m;
+    auto round_len = [&](const std::vector<int>& s, int r) {
+        int l = 0;
+        for (int i = 0; i < 32; ++i)
+            if (s[32 * r + i] >= 0) l = std::max(l, len_of[s[32 * r + i]]);
+        if ((l & 1) && l < f_n) ++l;
+        return l;
+    };
+    auto read_start = [&](int m, int Lr) { return std::min(lo_of[m] - f_lo, f_n - Lr); };
+    auto cost = [&](const std::vector<int>& s, int* taps_out) {
+        int total = 0, tp = 0;
+        for (int r = 0; r < 4; ++r) {
+            const int Lr = round_len(s, r);
+            tp += Lr;
+            if (Lr == 0) continue;
+            int wf = 0;
+            for (int h = 0; h < 2; ++h) {
+                int seen[16][8], cnt[16] = {0};
+                int worst = 1;
+                for (int i = 0; i < 16; ++i) {
+                    const int m = s[32 * r + 16 * h + i];
+                    if (m < 0) continue;   // an idle lane copies a neighbour's address (broadcast)
+                    const int st = f_lo + read_start(m, Lr), k = st & 15;
+                    bool dup = false;
+                    for (int j = 0; j < cnt[k]; ++j) dup = dup || seen[k][j] == st;
+                    if (!dup && cnt[k] < 8) seen[k][cnt[k]++] = st;
+                    worst = std::max(worst, cnt[k]);
+                }
+                wf += worst;
+            }
+            total += Lr * wf;
+        }
+        if (taps_out) *taps_out = tp;
+        return total;
+    };
+    {
+        int tp = 0;
+        int cur = cost(slot, &tp);
+        std::vector<int> best = slot;
+        int best_cost = cur;
+        uint32_t rng = 0x9e3779b9u;
+        auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+        double temp = 2.0;
+        const int used_rounds = (n_mel + 31) / 32;
+        const int iters = getenv("IRIS_MEL_NATURAL") ? 0 : 60000;   // A/B switch: filter m on lane m % 32 of round m / 32
+        for (int it = 0; it < iters && best_cost > 2 * taps; ++it) {
+            const int a = int(next() % uint32_t(32 * used_rounds)), b = int(next() % uint32_t(32 * used_rounds));
+            if (a == b || slot[a] == slot[b]) continue;
+            std::swap(slot[a], slot[b]);
+            int tp2 = 0;
+            const int cst = cost(slot, &tp2);
+            const bool ok = tp2 <= taps;
+            const double u = double(next() & 0xffff) / 65536.0;
+            if (ok && (cst <= cur || u < exp(double(cur - cst) / temp))) {
+                cur = cst;
+                if (cst < best_cost) { best_cost = cst; best = slot; }
+            } else {
+                std::swap(slot[a], slot[b]);
+            }
+            temp = std::max(0.05, temp * 0.9999);
+        }
+        slot = best;
+        for (int r = 0; r < 4; ++r) L[r] = round_len(slot, r);
+        taps = L[0] + L[1] + L[2] + L[3];
+        c->mel_read_wavefronts = best_cost;
+    }
+    // info word of a slot: first tap (relative to f_lo) | mel row << 16; row 0xffff = idle lane
+    std::vector<uint32_t> info(n_slots, 0xffff0000u);
     std::vector<float> fw(size_t(std::max(taps, 1)) * 32, 0.f);
     int row0 = 0;
     for (int r = 0; r < 4; ++r) {
-        for (int l = 0; l < 32; ++l) {
-            const int m = 32 * r + l;
-            if (m >= n_mel || lo_of[m] < 0) continue;
-            const int start = std::min(lo_of[m] - f_lo, f_n - L[r]);
-            info[m] = uint32_t(start);
-            for (int i = 0; i < len_of[m]; ++i)
-                fw[size_t(row0 + (lo_of[m] - f_lo - start) + i) * 32 + l] =
-                    w[size_t(lo_of[m] + i) * n_mel + m];
+        for (int h = 0; h < 2; ++h) {
+            int fill = 0;   // idle lanes read where the first busy lane of their half-warp reads
+            for (int i = 0; i < 16; ++i) {
+                const int m = slot[32 * r + 16 * h + i];
+                if (m >= 0) { fill = read_start(m, L[r]); break; }
+            }
+            for (int i = 0; i < 16; ++i) {
+                const int l = 16 * h + i, m = slot[32 * r + l];
+                if (m < 0) {
+                    info[32 * r + l] = 0xffff0000u | uint32_t(L[r] ? fill : 0);
+                    continue;
+                }
+                const int start = read_start(m, L[r]);
+                info[32 * r + l] = uint32_t(start) | (uint32_t(m) << 16);
+                for (int t = 0; t < len_of[m]; ++t)
+                    fw[size_t(row0 + (lo_of[m] - f_lo - start) + t) * 32 + l] =
+                        w[size_t(lo_of[m] + t) * n_mel + m];
+            }
         }
         row0 += L[r];
     }
@@ -727,11 +819,14 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     const size_t o_mf = o;   o = align_up(o + size_t(B) * n_extra * 4, 16);
     const size_t o_msf = o;  o = align_up(o + size_t(B) * n_extra * 4, 16);
     const size_t total = o;
-    if (c->h_stage) CU(cudaEventSynchronize(c->stage_free));   // previous upload done with it
-    rc = ensure_stage(c, total);
+    const int slot = c->stage_next;
+    c->stage_next = (slot + 1) % iris_ctx::kStageRing;
+    if (c->h_stage[slot]) CU(cudaEventSynchronize(c->stage_free[slot]));   // the upload that used it has drained
+    rc = ensure_stage(c, slot, total);
     if (rc) return rc;
+    if (total > c->plan_blob.cap) CU(cudaStreamSynchronize(st));   // kernels of earlier batches still read the old blob
     CU(c->plan_blob.reserve(total));
-    char* h = static_cast<char*>(c->h_stage);
+    char* h = static_cast<char*>(c->h_stage[slot]);
     memcpy(h + o_segs, c->h_segs.data(), c->h_segs.size() * sizeof(Seg));
     memcpy(h + o_ptr, c->h_seg_ptr.data(), size_t(B + 1) * 4);
     if (V > 0) {
@@ -749,7 +844,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         for (size_t i = 0; i < size_t(B) * n_extra; ++i) sf[i] = sqrtf(1.f - pl->merge_factor[i]);
     }
     CU(cudaMemcpyAsync(c->plan_blob.p, h, total, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(c->stage_free, st));
+    CU(cudaEventRecord(c->stage_free[slot], st));
     char* d = c->plan_blob.as<char>();
     c->d_segs = reinterpret_cast<Seg*>(d + o_segs);
     c->d_seg_ptr = reinterpret_cast<int32_t*>(d + o_ptr);

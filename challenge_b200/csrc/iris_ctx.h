@@ -89,9 +89,13 @@ struct iris_ctx {
     DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
     DevBuf tiles, sched;
     int max_segs = 1;
-    void* h_stage = nullptr;  // pinned staging for the plan blob
-    size_t h_stage_cap = 0;
-    cudaEvent_t stage_free = nullptr;
+    // pinned staging for the plan blob: a ring, so that the host can run up to kStageRing batches
+    // ahead of the device before it has to wait for an upload to drain
+    static constexpr int kStageRing = 4;
+    void* h_stage[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_stage_cap[kStageRing] = {0, 0, 0, 0};
+    cudaEvent_t stage_free[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
+    int stage_next = 0;
     // device views into plan_blob
     Seg* d_segs = nullptr;
     int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
@@ -106,6 +110,21 @@ struct iris_ctx {
     bool spec_mode = false;            // the uploaded plan mixes spectrogram banks
     int mel_bins = 0;
     bool mel_fusable = false;
+    // ---- one-call step (iris_step.cu) ----
+    cudaStream_t side = nullptr;       // metric leg: counting + count all-reduce beside the feature kernel
+    cudaEvent_t ev_labels = nullptr;   // labels of the current step are written
+    static constexpr int kLegRing = 8;
+    struct MetricLeg {
+        cudaEvent_t done = nullptr;
+        const void* labels = nullptr;  // frame-label buffer the leg reads
+        uint64_t seq = 0;              // iris_step call that issued it (1-based); 0: never used
+    } legs[kLegRing];
+    uint64_t step_seq = 0;
+    std::vector<int32_t> draw_i32;     // host draws of the last iris_step (views in `draws`)
+    std::vector<float> draw_f32;
+    iris_draws draws{};
+    int mel_read_wavefronts = 0;       // modelled shared-memory wavefronts per frame of the mel tap reads
 };
 
 int iris_set_device(iris_ctx* c);
+void iris_step_release(iris_ctx* c);   // iris_step.cu: side stream + events

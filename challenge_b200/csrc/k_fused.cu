@@ -40,7 +40,7 @@
 namespace iris {
 
 constexpr int kRing = 8;         // TileBlock ring entries (> stage buffers + 1, see the producer)
-constexpr int kMaxStages = 16;   // mixing segments of one clip (upper bound on stages per tile)
+constexpr int kMaxStages = 24;   // mixing segments of one clip (upper bound on stages per tile; the ring copy takes <= 30)
 #ifndef IRIS_MAX_FR
 #define IRIS_MAX_FR 16
 #endif
@@ -255,6 +255,9 @@ __device__ __forceinline__ void store_piece(const FusedParams& p, int b, int f, 
 // per-round flag branches, no odd-channel selects, C folded into the address arithmetic, the
 // projection loops unrolled to their 12 taps.  Measured: plain mel 202 -> 190 us.
 constexpr int EPI_MINMAX = 1, EPI_LOG = 2, EPI_C2 = 4;
+#ifndef IRIS_FIX_FR
+#define IRIS_FIX_FR 8   // frames per tile of the fixed mel variants (experiment builds: 9 = 10 warps per CTA)
+#endif
 __host__ __device__ constexpr int fixed_mel_L(int r) { return r == 0 ? 2 : (r == 1 ? 4 : (r == 2 ? 6 : 0)); }
 template <int MODE, int NJ, int EPI>
 __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ FusedParams p) {
@@ -270,7 +273,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const int warp = tid >> 5, lane = tid & 31;
     // fixed variants: 8 frames per tile and the 12 taps of the default mel shape, so that the
     // shared-memory map folds into immediates
-    const int FR = kFix ? 8 : p.fr;
+    const int FR = kFix ? IRIS_FIX_FR : p.fr;
     const int mel_taps = kFix ? (fixed_mel_L(0) + fixed_mel_L(1) + fixed_mel_L(2)) : p.mel_taps;
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
     uint64_t* empty = reinterpret_cast<uint64_t*>(sm + OFF_EMPTY);
@@ -289,7 +292,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         }
         if (kMel) {
             uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
-            for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = i < p.n_mel ? p.mel_info[i] : 0u;
+            for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = p.mel_info[i];   // [4 rounds][32 lanes]
             float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
             for (int i = tid; i < mel_taps * 32; i += blockDim.x) s_mw[i] = p.mel_w[i];
         }
@@ -415,10 +418,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         const uint64_t pol_keep = l2_policy_evict_last();
         // mel rows are re-read by k_logmel_post: keep them in L2 (fixed variants: hints are on)
         const bool keep_l2 = kFix ? bool(EPI & EPI_MINMAX) : (kMel && p.l2_hints && do_minmax);
-        float* clip_out = p.out;      // out[b, m = lane, 0, 0] of the current clip (mel modes)
+        float* clip_out = p.out;      // out[b, 0, 0, 0] of the current clip (mel modes)
         uint32_t zbits = 0;
         int zb_clip = -1;
-        const size_t lane_off = size_t(lane) * p.T * C;          // out[b, m = lane + 32 r, t, c]
         const size_t clip_elems = size_t(p.n_mel) * p.T * C;
         for (int i = 0;; ++i) {
             const TileBlock* tb = reinterpret_cast<const TileBlock*>(sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes);
@@ -428,6 +430,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             const int4 hdr = *reinterpret_cast<const int4*>(tb);
             const int n_st = hdr.x;
             if (n_st == 0) break;                    // end marker
+            // (skipping the row reads of time-masked frames -- ~11 % of the frames -- was measured on
+            // B200: +2..5 % kernel time; the extra branch costs registers (93 -> 96 + a spill) and the
+            // kernel is bound by issue latency at 4.4 warps per scheduler, not by shared-memory wavefronts)
             {
                 const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[0].j_lo);   // j_lo | j_cnt << 16, gain
                 const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
@@ -475,7 +480,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             // bit 8 -> bin 256.  Recomputed when the clip changes.
             if (b != zb_clip) {
                 zb_clip = b;
-                if (kMel) clip_out = p.out + size_t(b) * clip_elems + lane_off;
+                if (kMel) clip_out = p.out + size_t(b) * clip_elems;
                 zbits = 0;
                 const int4 fmv = *reinterpret_cast<const int4*>(tb->fm);
                 if (kMel && NJ == 4) {
@@ -547,7 +552,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 // of the warp's 4352-byte exchange rows): no range checks on the way in
                 float2* mg = reinterpret_cast<float2*>(xch);
                 const int f_lo = p.mel_f_lo;
-                float acc0[4], acc1[4];   // mel bins m = lane + 32 r
+                float acc0[4], acc1[4];   // mel filter of slot (round r, lane): iris_set_mel's assignment
+                const uint32_t* ms = reinterpret_cast<const uint32_t*>(sm + OFF_MSTART) + lane;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
                 if (do_fft) {   // warp-uniform
@@ -568,16 +574,15 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         if (l0) emit(256, 8, z8, z8);
                     }
                     __syncwarp();
-                    // sparse mel projection (transforms.py:51-77): filter m = lane + 32 r reads
-                    // mel_L[r] taps starting at its first bin; shorter filters are zero-padded,
-                    // so the trip count is uniform across the warp
+                    // sparse mel projection (transforms.py:51-77): the filter of slot (r, lane) reads
+                    // mel_L[r] taps starting at its first bin (low half of the slot's info word);
+                    // shorter filters are zero-padded, so the trip count is uniform across the warp
                     const float* wr = reinterpret_cast<const float*>(sm + OFF_MW) + lane;
-                    const uint32_t* ms = reinterpret_cast<const uint32_t*>(sm + OFF_MSTART) + lane;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int L = kFix ? fixed_mel_L(r) : p.mel_L[r];   // 0 for r >= ceil(n_mel / 32); uniform
                         if (L == 0) break;
-                        const float2* a = mg + f_lo + ms[32 * r];
+                        const float2* a = mg + f_lo + (ms[32 * r] & 0xffffu);
                         cpx sacc{0.f, 0.f};   // (ch0, ch1)
 #pragma unroll
                         for (int q = 0; q < kMaxFilter; q += 2) {   // L is even (iris_set_mel pads)
@@ -596,14 +601,15 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 }
                 // ---- every lane stores its own mel values: out[b, m, t, 2*pair .. +1] ----
                 if (in_range) {
-                    float* o = clip_out + t * C + 2 * pair;
-                    const size_t rs32 = size_t(32) * p.T * C;
+                    float* o_t = clip_out + t * C + 2 * pair;
+                    const uint32_t row_elems = uint32_t(p.T) * uint32_t(C);
                     const bool lg = do_lg;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        if (kFix ? (fixed_mel_L(r) == 0) : (32 * r >= p.n_mel)) break;   // uniform: no work behind the last round
-                        // fixed variants: 64 < n_mel <= 96, only the third round is partial
-                        if ((kFix && r < 2) || lane + 32 * r < p.n_mel) {
+                        if (kFix ? (fixed_mel_L(r) == 0) : (p.mel_L[r] == 0)) break;   // uniform: no work behind the last round
+                        const uint32_t mrow = ms[32 * r] >> 16;   // mel row of this slot; 0xffff: idle lane
+                        if (mrow != 0xffffu) {
+                            float* o = o_t + mrow * row_elems;
                             float a0 = acc0[r], a1 = acc1[r];
                             if (do_minmax) {
                                 mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
@@ -621,7 +627,6 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                                 if (has1) o[1] = a1;
                             }
                         }
-                        o += rs32;
                     }
                 }
             } else if (MODE == FM_ACTIVITY) {
@@ -731,7 +736,7 @@ int fused_max_frames_per_tile() { return kMaxFR; }
 // other's load waits) measured fastest on B200: cfg2 mel 216 us vs 228 us for FR = 16 x 1 CTA
 // and 271 us for FR = 20 at 80 registers (spills).  IRIS_FR overrides it for experiments.
 int fused_pick_fr(int T, int mel_taps) {
-    int want = 8;
+    int want = mel_taps > 0 ? IRIS_FIX_FR : 8;
     if (const char* e = getenv("IRIS_FR")) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxFR) want = v;
@@ -758,6 +763,7 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
     const long long n_tiles = (long long)p.B * p.n_pairs * tpc;
     if (n_tiles <= 0) return cudaSuccess;
     if (n_tiles > 0x7fffffffLL || p.max_segs > kMaxStages || p.n_pairs > 127) return cudaErrorInvalidValue;
+    if (mode == FM_MEL && (long long)p.n_mel * p.T * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;   // 32-bit row offsets inside a clip
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
@@ -817,8 +823,8 @@ cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream
         case FM_MEL:
             if (p.mel_f_lo + p.mel_f_n > 128) IRIS_LAUNCH(FM_MEL, 8, 0)
             else if (p.C != 2 || p.mel_L[0] != fixed_mel_L(0) || p.mel_L[1] != fixed_mel_L(1) ||
-                     p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) || p.n_mel <= 64 ||
-                     !p.l2_hints || FR != 8 || p.mel_taps != 12 || getenv("IRIS_NO_FIXED_EPI"))
+                     p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) ||
+                     !p.l2_hints || FR != IRIS_FIX_FR || p.mel_taps != 12 || getenv("IRIS_NO_FIXED_EPI"))
                 IRIS_LAUNCH(FM_MEL, 4, 0)
             else if (p.do_minmax) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_MINMAX)
             else if (p.do_log) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_LOG)

@@ -57,6 +57,9 @@ class Engine:
         self._plan = None
 
     def close(self):
+        for p, n in getattr(self, '_host_allocs', []):
+            self.lib.iris_host_free(self._ctx, p, n)
+        self._host_allocs = []
         if self._ctx:
             self.lib.iris_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
@@ -222,6 +225,151 @@ class Engine:
             assert tuple(out.shape) == shape and out.is_contiguous() and out.is_cuda
         L.check(self.lib.iris_features_select(self._ctx, int(mode), int(select), self._ptr(out), self._stream()))
         return out
+
+    # ---- one call per batch (iris_step) ----
+    def step_config(self, draw_cfg, mode, stft_filter=0, chan_remap=L.REMAP_NONE, n_out_chan=0):
+        return L.IrisStepConfig(draw_cfg, int(stft_filter), int(chan_remap), int(n_out_chan), int(mode))
+
+    def step(self, scfg, uniforms, streams=None, out=None, frame=None, want_frame=True, vtk=None,
+             keep=None, y_pred=None, triples=None, counts=None, comm=None, counts_reduced=None,
+             triples_send=None, triples_global=None, global_batch=0, threshold=0.5):
+        """ONE C call: draws from ``uniforms`` -> plan upload -> labels -> features, plus the metric
+        leg (counting, count all-reduce) on the context's side stream when ``y_pred`` is given.
+        -> (features, frame_labels or None).  ``streams``: ``plan.stream_handles(...)``."""
+        torch = _torch()
+        g = scfg.draw
+        B, T, V = g.batch, g.n_frame, g.max_voices
+        c_out = self.bank_chan
+        if scfg.chan_remap == L.REMAP_STEREO_MONO:
+            c_out = 3
+        elif scfg.chan_remap == L.REMAP_MERGE_AUG:
+            c_out = int(scfg.n_out_chan)
+        self._plan = dict(B=B, T=T, V=V, c_out=c_out, bytes=0)
+        mode = scfg.feature_mode
+        shape = self.feature_shape(mode)
+        if out is None:
+            out = self._empty(shape)
+        else:
+            assert tuple(out.shape) == shape and out.is_contiguous() and out.is_cuda
+        if frame is None and want_frame and V > 0:
+            frame = self._empty((B, T, self.n_classes))
+        u = uniforms if uniforms.flags['C_CONTIGUOUS'] and uniforms.dtype == np.float64 \
+            else np.ascontiguousarray(uniforms, np.float64)
+        io = L.IrisStepIO()
+        io.uniforms = u.ctypes.data
+        if streams is not None:
+            io.streams = streams
+        io.d_features = out.data_ptr()
+        io.d_frame_labels = frame.data_ptr() if frame is not None else None
+        io.d_labels_vtk = vtk.data_ptr() if vtk is not None else None
+        io.d_keep = keep.data_ptr() if keep is not None else None
+        if y_pred is not None:
+            io.d_y_pred = y_pred.data_ptr()
+            io.threshold = float(threshold)
+            io.d_triples = triples.data_ptr()
+            io.d_counts = counts.data_ptr() if counts is not None else None
+            if comm is not None:
+                io.comm = comm
+                io.d_counts_reduced = counts_reduced.data_ptr()
+                io.d_triples_send = triples_send.data_ptr() if triples_send is not None else None
+                io.d_triples_global = triples_global.data_ptr() if triples_global is not None else None
+                io.global_batch = int(global_batch)
+        L.check(self.lib.iris_step(self._ctx, C.byref(scfg), C.byref(io), self._stream()))
+        return out, frame
+
+    def counts_wait(self, lag=0):
+        """The current stream waits for the metric leg issued ``lag`` steps ago."""
+        L.check(self.lib.iris_counts_wait(self._ctx, int(lag), self._stream()))
+
+    def step_draws(self, scfg):
+        """The draws of the last ``step`` as a :class:`BatchDraws` (copies)."""
+        g = scfg.draw
+        B, V, M = g.batch, g.max_voices, g.max_noises
+        raw = L.IrisDraws()
+        L.check(self.lib.iris_step_draws(self._ctx, C.byref(raw)))
+
+        def arr(name, shape):
+            ptr = getattr(raw, name)
+            if not ptr:
+                return None
+            return np.ctypeslib.as_array(ptr, shape=shape).copy()
+        d = BatchDraws(batch=B, n_frame=g.n_frame, max_voices=V, max_noises=M, bg_id=arr('bg_id', (B,)),
+                       bg_offset=arr('bg_offset', (B,)), min_ratio=g.min_ratio,
+                       min_noise_ratio=g.min_noise_ratio)
+        if V > 0:
+            d.n_voices, d.voice_id = arr('n_voices', (B,)), arr('voice_id', (B, V))
+            d.voice_u, d.voice_gain = arr('voice_u', (B, V)), arr('voice_gain', (B, V))
+            d.voice_offset = arr('voice_offset', (B, V))
+        if M > 0:
+            d.n_noises, d.noise_id = arr('n_noises', (B,)), arr('noise_id', (B, M))
+            d.noise_u, d.noise_gain = arr('noise_u', (B, M)), arr('noise_gain', (B, M))
+            d.noise_offset = arr('noise_offset', (B, M))
+        if g.n_time_masks:
+            d.time_masks = arr('time_masks', (B, g.n_time_masks, 2))
+        if g.n_freq_masks:
+            d.freq_masks = arr('freq_masks', (B, g.n_freq_masks, 2))
+        if g.merge_extra:
+            d.merge_factor = arr('merge_factor', (B, g.merge_extra))
+        return d
+
+    def mel_fusable(self):
+        return bool(self.lib.iris_mel_fusable(self._ctx))
+
+    # ---- DLPack hand-over ----
+    def features_dlpack(self, mode, capsule):
+        """``iris_features`` into the tensor behind a DLPack capsule (``to_dlpack(t)``)."""
+        L.check(self.lib.iris_features_dlpack(self._ctx, int(mode), L.dlpack_pointer(capsule), self._stream()))
+
+    def step_dlpack(self, scfg, uniforms, features_capsule, frame_capsule=None, streams=None):
+        u = np.ascontiguousarray(uniforms, np.float64)
+        g = scfg.draw
+        c_out = self.bank_chan
+        if scfg.chan_remap == L.REMAP_STEREO_MONO:
+            c_out = 3
+        elif scfg.chan_remap == L.REMAP_MERGE_AUG:
+            c_out = int(scfg.n_out_chan)
+        self._plan = dict(B=g.batch, T=g.n_frame, V=g.max_voices, c_out=c_out, bytes=0)
+        L.check(self.lib.iris_step_dlpack(
+            self._ctx, C.byref(scfg), u.ctypes.data, streams, L.dlpack_pointer(features_capsule),
+            L.dlpack_pointer(frame_capsule) if frame_capsule is not None else None, self._stream()))
+
+    # ---- multi-GPU: the count all-reduce (NCCL inside libiris) ----
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        L.check(self.lib.iris_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_comm(self, unique_id, rank, world_size):
+        comm = C.c_void_p()
+        L.check(self.lib.iris_nccl_comm_create(self._ctx, unique_id, int(rank), int(world_size), C.byref(comm)))
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        L.check(self.lib.iris_nccl_comm_destroy(comm))
+
+    def allreduce_counts(self, comm, counts_send, counts_recv, triples_send=None, triples_recv=None,
+                         global_batch=0):
+        L.check(self.lib.iris_allreduce_counts(
+            self._ctx, comm, self._ptr(counts_send), self._ptr(counts_recv), self._ptr(triples_send),
+            self._ptr(triples_recv), int(global_batch), self._stream()))
+
+    def er_from_triples(self, triples):
+        """metrics.py:268-273 on (reduced) triples ``[n,3]`` int32 -> er ``[n]``."""
+        er = self._empty((triples.shape[0],))
+        L.check(self.lib.iris_er_from_triples(self._ctx, self._ptr(triples), int(triples.shape[0]),
+                                              self._ptr(er), self._stream()))
+        return er
+
+    def host_alloc(self, shape, dtype=np.float32):
+        """Pinned host array on the NUMA node of this GPU (``iris_host_alloc``) -> (ndarray, node)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p, node = C.c_void_p(), C.c_int(-1)
+        L.check(self.lib.iris_host_alloc(self._ctx, n, C.byref(p), C.byref(node)))
+        buf = (C.c_char * n).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._host_allocs = getattr(self, '_host_allocs', [])
+        self._host_allocs.append((p, n))
+        return a, node.value
 
     def plan_bytes(self, mode, keep=None):
         bi, bo = C.c_int64(), C.c_int64()

@@ -24,8 +24,8 @@ import numpy as np
 
 from . import _lib as L
 from . import _ops as O
-from .engine import get_engine
-from .plan import ShuffleStream, draw_batch
+from .engine import Engine, get_engine
+from .plan import ShuffleStream, draw_batch, draw_config, stream_handles, uniforms_per_clip
 
 AUTOTUNE = -1   # tf.data.experimental.AUTOTUNE stand-in for .prefetch()
 
@@ -35,23 +35,35 @@ def _is_waveform_bank(items):
 
 
 class IrisDataset:
-    """Lazy description of ``make_pipeline(...)`` followed by ``map`` / ``batch`` stages."""
+    """Lazy description of ``make_pipeline(...)`` followed by ``map`` / ``batch`` / ``take`` stages.
 
-    def __init__(self, source, stages=(), batch_size=None, limit=None):
+    Every pipeline owns its engine (= its ``iris_ctx`` and bank set), so a train and a test
+    pipeline built back to back (sj_train.py:472-473, trainer.py:261-262) stay independent."""
+
+    def __init__(self, source, stages=(), batch_size=None, limit=None, elem_limit=None,
+                 drop_remainder=False):
         self._src = source
         self._stages = tuple(stages)        # callables; ('batch', n) marks the batch point
         self._batch = batch_size
-        self._limit = limit
+        self._limit = limit                 # take() after batch(): batches
+        self._elem_limit = elem_limit       # take() before batch(): elements, as in tf.data
+        self._drop_remainder = drop_remainder
+
+    def _with(self, **kw):
+        args = dict(source=self._src, stages=self._stages, batch_size=self._batch, limit=self._limit,
+                    elem_limit=self._elem_limit, drop_remainder=self._drop_remainder)
+        args.update(kw)
+        return IrisDataset(**args)
 
     # ---- tf.data surface used by sj_train.make_dataset ----
     def map(self, fn, num_parallel_calls=None):
-        return IrisDataset(self._src, self._stages + (fn,), self._batch, self._limit)
+        return self._with(stages=self._stages + (fn,))
 
     def batch(self, batch_size, drop_remainder=False):
         if self._batch is not None:
             raise ValueError('IrisDataset is already batched')
-        return IrisDataset(self._src, self._stages + (('batch', int(batch_size)),),
-                           int(batch_size), self._limit)
+        return self._with(stages=self._stages + (('batch', int(batch_size)),), batch_size=int(batch_size),
+                          drop_remainder=bool(drop_remainder))
 
     def prefetch(self, buffer_size=None):
         return self
@@ -63,10 +75,19 @@ class IrisDataset:
         return self      # the source streams are already shuffled (pipeline.py:147,154,164)
 
     def take(self, count):
-        return IrisDataset(self._src, self._stages, self._batch, int(count))
+        count = int(count)
+        if self._batch is None:             # elements, like tf.data; batch() then sees `count` of them
+            cur = self._elem_limit
+            return self._with(elem_limit=count if cur is None else min(cur, count))
+        cur = self._limit
+        return self._with(limit=count if cur is None else min(cur, count))
+
+    @property
+    def engine(self):
+        return self._src['engine']
 
     # ---- lowering ----
-    def _lower(self):
+    def _lower(self, allow_mel=True):
         """Split the stage list into what the fused kernel absorbs and the remainder."""
         fused = dict(frame_labels=False, density_labels=False, augment=False, remap=L.REMAP_NONE, n_out=0, filt=0,
                      mode=L.FEAT_COMPLEX, n_mels=0, mel_matrix=None)
@@ -100,7 +121,7 @@ class IrisDataset:
                 state = 'post'
             elif state == 'post' and tag and tag[0] == 'magphase' and fused['mode'] == L.FEAT_COMPLEX:
                 fused['mode'] = L.FEAT_MAGPHASE
-            elif state == 'post' and tag and tag[0] == 'mel' and fused['mode'] == L.FEAT_MAGPHASE \
+            elif state == 'post' and allow_mel and tag and tag[0] == 'mel' and fused['mode'] == L.FEAT_MAGPHASE \
                     and fused['remap'] == L.REMAP_NONE:
                 fused['mode'], fused['n_mels'], fused['mel_matrix'] = L.FEAT_MEL, tag[1], tag[2]
             elif state == 'post' and tag and tag[0] == 'minmax' and fused['mode'] == L.FEAT_MEL \
@@ -116,30 +137,78 @@ class IrisDataset:
             i += 1
         return fused, rest
 
-    def __iter__(self):
+    def _prepare(self):
+        """Lower the stage list once per iteration: fused step configuration + leftover stages."""
         src = self._src
         eng = src['engine']
         fused, rest = self._lower()
+        if fused['mode'] >= L.FEAT_MEL:
+            cur = eng.mel_matrix
+            if cur is None or cur.shape != fused['mel_matrix'].shape \
+                    or not np.array_equal(cur, fused['mel_matrix']):
+                eng.set_mel(mel_matrix=fused['mel_matrix'])
+            if not src['spec_banks'] and not eng.mel_fusable():
+                # a filter wider than the fused epilogue takes (e.g. n_mels = 20): the fused kernel
+                # stops at magnitude + phase and the mel stage runs as the stand-alone kernel
+                fused, rest = self._lower(allow_mel=False)
+        # stages the fused launch did not absorb: the ones mapped BEFORE .batch() see single
+        # elements in the reference, so they run per element here (then the batch is re-stacked)
+        pre, post = [], []
+        seen_batch = not any(isinstance(st, tuple) and st[0] == 'batch' for st in rest)
+        for st in rest:
+            if isinstance(st, tuple) and st[0] == 'batch':
+                seen_batch = True
+                continue
+            (post if seen_batch and self._batch is not None else pre).append(st)
+        return fused, pre, post
+
+    def _step_config(self, fused, B):
+        src = self._src
+        cfg = draw_config(B, src['n_frame'], src['max_voices'], src['max_noises'], src['snr'],
+                          src['min_ratio'], src['min_noise_ratio'],
+                          6 if fused['augment'] else 0, 24, 1 if fused['augment'] else 0, 16, 257,
+                          max(fused['n_out'] - 2, 0) if fused['remap'] == L.REMAP_MERGE_AUG else 0)
+        return src['engine'].step_config(cfg, fused['mode'], stft_filter=fused['filt'],
+                                         chan_remap=fused['remap'], n_out_chan=fused['n_out'])
+
+    def __iter__(self):
+        src = self._src
+        eng = src['engine']
+        fused, pre, post = self._prepare()
         B = self._batch or 1
-        n = 0
-        while self._limit is None or n < self._limit:
-            d = draw_batch(O.rng(), B, src['n_frame'], src['bg_frames'], src['voice_frames'],
-                           src['noise_frames'], max_voices=src['max_voices'],
-                           max_noises=src['max_noises'], snr=src['snr'], min_ratio=src['min_ratio'],
-                           min_noise_ratio=src['min_noise_ratio'],
-                           n_time_masks=6 if fused['augment'] else 0, time_mask_max=24,
-                           n_freq_masks=1 if fused['augment'] else 0, freq_mask_max=16,
-                           merge_extra=max(fused['n_out'] - 2, 0) if fused['remap'] == L.REMAP_MERGE_AUG else 0,
-                           streams=src['streams'])
-            if fused['mode'] >= L.FEAT_MEL:
-                cur = eng.mel_matrix
-                if cur is None or cur.shape != fused['mel_matrix'].shape \
-                        or not np.array_equal(cur, fused['mel_matrix']):
-                    eng.set_mel(mel_matrix=fused['mel_matrix'])
-            eng.upload_plan(d, stft_filter=fused['filt'], chan_remap=fused['remap'],
-                            n_out_chan=fused['n_out'])
-            frame, vtk, _ = eng.labels(want_vtk=not fused['frame_labels'], want_keep=False)
-            x = eng.features(fused['mode'])
+        handles = stream_handles(src['streams'])
+        configs = {}
+
+        def config_for(b):
+            if b not in configs:
+                sc = self._step_config(fused, b)
+                configs[b] = (sc, uniforms_per_clip(sc.draw))
+            return configs[b]
+
+        def _el(t, i):
+            return tuple(u[i] for u in t) if isinstance(t, tuple) else t[i]
+
+        def _stack(items):
+            import torch
+            if isinstance(items[0], tuple):
+                return tuple(torch.stack([it[k] for it in items]) for k in range(len(items[0])))
+            return torch.stack(list(items))
+
+        n_batches = 0
+        elems_left = self._elem_limit
+        while self._limit is None or n_batches < self._limit:
+            b = B
+            if elems_left is not None:
+                if elems_left <= 0 or (elems_left < B and self._drop_remainder):
+                    break
+                b = min(B, elems_left)
+                elems_left -= b
+            scfg, n_u = config_for(b)
+            want_vtk = not fused['frame_labels'] or fused['density_labels']
+            vtk = eng._empty((b, src['max_voices'], src['n_frame'], eng.n_classes)) if want_vtk else None
+            # ONE C call: draws -> plan -> labels -> features (include/iris.h iris_step)
+            x, frame = eng.step(scfg, O.rng().random((b, n_u)), streams=handles, vtk=vtk,
+                                want_frame=fused['frame_labels'])
             y = frame if fused['frame_labels'] else vtk
             if fused['density_labels']:
                 from .trainer import to_density_labels
@@ -147,29 +216,9 @@ class IrisDataset:
             if src.get('separate'):   # (label, only_voice, only_noise), pipeline.py:107-108
                 y = (y, eng.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES),
                      eng.features(L.FEAT_COMPLEX, select=L.SELECT_BG_NOISE))
-            # stages the fused launch did not absorb: the ones mapped BEFORE .batch() see single
-            # elements in the reference, so they run per element here (then the batch is re-stacked)
-            pre = []
-            post = []
-            # a .batch() that the lowering absorbed leaves only post-batch stages in `rest`
-            seen_batch = not any(isinstance(st, tuple) and st[0] == 'batch' for st in rest)
-            for st in rest:
-                if isinstance(st, tuple) and st[0] == 'batch':
-                    seen_batch = True
-                    continue
-                (post if seen_batch and self._batch is not None else pre).append(st)
-
-            def _el(t, i):
-                return tuple(u[i] for u in t) if isinstance(t, tuple) else t[i]
-
-            def _stack(items):
-                import torch
-                if isinstance(items[0], tuple):
-                    return tuple(torch.stack([it[k] for it in items]) for k in range(len(items[0])))
-                return torch.stack(list(items))
             if pre:
                 xs, ys = [], []
-                for i in range(B):
+                for i in range(b):
                     xi, yi = _el(x, i), _el(y, i)
                     for st in pre:
                         res = st(xi, yi)
@@ -182,8 +231,20 @@ class IrisDataset:
             for st in post:
                 res = st(x, y)
                 x, y = res if isinstance(res, tuple) and len(res) == 2 else (res, y)
-            n += 1
+            n_batches += 1
             yield x, y
+
+
+_merge_engines = {}
+
+
+def _merge_engine():
+    """Engine of the single-sample ``merge_complex_specs`` calls (one per device)."""
+    import torch
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if dev not in _merge_engines:
+        _merge_engines[dev] = Engine(dev)
+    return _merge_engines[dev]
 
 
 def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300, n_classes=3,
@@ -203,7 +264,7 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
         raise ValueError('background must be a spectrogram [freq, time, chan2] or a waveform [chan, samples]')
     if t_axis != 1:
         raise NotImplementedError('merge_complex_specs: t_axis must be 1 (the only value the reference uses)')
-    eng = get_engine()
+    eng = _merge_engine()     # not a pipeline's engine: live datasets keep their banks
     bf = eng.register_bank(L.BANK_BG, [background])
     vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
     nf = eng.register_bank(L.BANK_NOISE, list(noises)) if noises is not None else None
@@ -247,10 +308,25 @@ def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan,
     assert len(voices) == len(labels)
     assert len(np.asarray(labels[0]).shape) == 1 and np.asarray(labels[0]).shape[0] == n_classes, \
         'labels must be in the form of [n_samples, n_classes]'
-    eng = get_engine()
+    import torch
+    eng = Engine(torch.cuda.current_device() if torch.cuda.is_available() else 0)   # this pipeline's bank set
     bf = eng.register_bank(L.BANK_BG, list(backgrounds))
     vf = eng.register_bank(L.BANK_VOICE, list(voices), labels=np.asarray(labels, np.float32))
     nf = eng.register_bank(L.BANK_NOISE, list(noises)) if noises is not None else None
+    spec_banks = not _is_waveform_bank(backgrounds)
+    V, M = int(max_voices), int(max_noises) if noises is not None else 0
+    if not spec_banks:
+        # the fused kernel mixes at most iris_max_segments() source segments per clip: background
+        # tiles (pipeline.py:29-35) + accepted voices (< max_voices) + noises (< max_noises)
+        reps = -(-int(n_frame) // int(min(bf)))
+        worst = (reps + 1) + max(V - 1, 1) + max(M - 1, 0)
+        cap = int(eng.lib.iris_max_segments())
+        if worst > cap:
+            raise ValueError(
+                'make_pipeline: a clip could mix %d segments (%d background tiles of the shortest '
+                'background (%d frames < n_frame=%d), %d voices, %d noises); the fused kernel takes '
+                '%d.  Use longer backgrounds, fewer max_voices / max_noises, or spectrogram banks.'
+                % (worst, reps + 1, int(min(bf)), int(n_frame), max(V - 1, 1), max(M - 1, 0), cap))
     r = O.rng()
     streams = {'bg': ShuffleStream(len(backgrounds), r), 'voice': ShuffleStream(len(voices), r)}
     if noises is not None:
@@ -259,5 +335,5 @@ def make_pipeline(backgrounds,  # a list of background noises  (waveforms [chan,
                   max_voices=int(max_voices), max_noises=int(max_noises) if noises is not None else 0,
                   snr=kwargs.get('snr', -20), min_ratio=kwargs.get('min_ratio', 2 / 3),
                   min_noise_ratio=kwargs.get('min_noise_ratio', 1 / 2), streams=streams,
-                  separate=bool(kwargs.get('seperate_noise_voice', False)))
+                  separate=bool(kwargs.get('seperate_noise_voice', False)), spec_banks=spec_banks)
     return IrisDataset(source)

@@ -15,13 +15,14 @@
 #ifndef IRIS_H_
 #define IRIS_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define IRIS_ABI_VERSION 1
+#define IRIS_ABI_VERSION 2
 
 typedef struct iris_ctx iris_ctx;
 typedef void* iris_stream; /* cudaStream_t */
@@ -292,6 +293,153 @@ int iris_op_eval_events(iris_ctx* ctx, const float* d_y, int L, int K, int hop, 
 int iris_op_get_er(iris_ctx* ctx, const int32_t* d_gt, int m, const int32_t* d_pred, int pred_stride,
                    int pred_time_col, const int32_t* d_n_pred, int n_pred_max, int32_t* d_out,
                    iris_stream stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One call per batch (round 2).  The reference builds a batch with ~B * (V + M + 10) tf.random
+ * draws inside merge_complex_specs / mask / random_merge_aug and ~10 Python-level tf.data stages
+ * (pipeline.py:113-175, sj_train.py:92-130).  Here the caller supplies ONE block of host
+ * uniforms per batch (randomness stays host-generated and explicit); iris_draw_batch turns it
+ * into the draws of an iris_plan with the reference's placement arithmetic, and iris_step runs
+ * draws -> plan upload -> labels -> features (-> metric counts -> count all-reduce) from C.
+ * --------------------------------------------------------------------------------------- */
+
+/* Dataset.from_generator(items).repeat().shuffle(buffer_size) as a stream of item ids
+ * (pipeline.py:143-147, 149-154, 159-164): a buffer fed by the endlessly repeated sequence
+ * 0..n-1; every draw emits slot floor(u * buffer_size) and refills it.  Host-only state. */
+typedef struct iris_shuffle iris_shuffle;
+int iris_shuffle_create(int n_items, int buffer_size, iris_shuffle** out);
+int iris_shuffle_destroy(iris_shuffle* s);
+int iris_shuffle_take(iris_shuffle* s, const double* uniforms, int k, int32_t* out_ids);
+
+typedef struct iris_draw_config {
+    int32_t batch;            /* B */
+    int32_t n_frame;          /* T */
+    int32_t max_voices;       /* V (0: none) */
+    int32_t max_noises;       /* M (0: none) */
+    float min_ratio;          /* merge_complex_specs min_ratio (pipeline.py:12) */
+    float min_noise_ratio;    /* (pipeline.py:13) */
+    float snr;                /* (pipeline.py:14): voice gain 10^-u, u ~ U[0, -snr/10) */
+    int32_t n_time_masks;     /* augment: 6 masks below time_mask_max = 24 (data_utils.py:59) */
+    int32_t time_mask_max;
+    int32_t n_freq_masks;     /* augment: 1 mask below freq_mask_max = 16 (data_utils.py:60) */
+    int32_t freq_mask_max;
+    int32_t n_bins;           /* 257 */
+    int32_t merge_extra;      /* random_merge_aug(number): number - 2 factors (data_utils.py:109) */
+} iris_draw_config;
+
+/* Uniforms one clip consumes, in the reference's per-clip draw order:
+ *   bg id, bg crop offset (pipeline.py:35), V voice ids, n_voices (43), V x {gain u (50),
+ *   offset (69)}, M noise ids, n_noises (87), M x {gain u (94), crop offset (103)},
+ *   n_time_masks x {size (transforms.py:25), offset (26)}, n_freq_masks x {size, offset},
+ *   merge_extra factors.  Integers are floor(u * range); ids come from the shuffle streams
+ *   when given. */
+int iris_draw_uniforms_per_clip(const iris_draw_config* cfg);
+
+/* Caller-allocated HOST outputs of iris_draw_batch; shapes as in iris_plan.  voice_u / noise_u
+ * are the raw fp32 exponent draws (gain = powf(10, -u)); rows behind n_voices / n_noises are
+ * zero (gain 1).  Pointers of absent parts (V == 0, no masks, ...) may be NULL. */
+typedef struct iris_draws {
+    int32_t* bg_id;        int32_t* bg_offset;
+    int32_t* n_voices;     int32_t* voice_id;   float* voice_u;  float* voice_gain;  int32_t* voice_offset;
+    int32_t* n_noises;     int32_t* noise_id;   float* noise_u;  float* noise_gain;  int32_t* noise_offset;
+    int32_t* time_masks;   int32_t* freq_masks;
+    float* merge_factor;
+} iris_draws;
+
+/* Host-only (no device needed): uniforms [batch, iris_draw_uniforms_per_clip] in [0, 1) ->
+ * draws.  *_frames are the frame counts of the bank items (1 + n_samples / 256, or the
+ * spectrogram lengths); streams[kind] may be NULL (ids = floor(u * n_items)).  Returns
+ * IRIS_ERR_EMPTY_RANGE where the reference's int-uniform would raise (pipeline.py:68-69). */
+int iris_draw_batch(const iris_draw_config* cfg, const int32_t* bg_frames, int n_bg,
+                    const int32_t* voice_frames, int n_voice, const int32_t* noise_frames, int n_noise,
+                    iris_shuffle* const* streams /* [3] or NULL */, const double* uniforms,
+                    iris_draws* out);
+
+typedef struct iris_step_config {
+    iris_draw_config draw;
+    int32_t stft_filter;      /* data_utils.stft_filter(k); 0 = off */
+    int32_t chan_remap;       /* IRIS_REMAP_* */
+    int32_t n_out_chan;       /* channels after remap */
+    int32_t feature_mode;     /* IRIS_FEAT_* */
+} iris_step_config;
+
+typedef void* iris_nccl_comm; /* ncclComm_t */
+
+typedef struct iris_step_io {
+    const double* uniforms;   /* HOST [batch, iris_draw_uniforms_per_clip(&cfg->draw)] */
+    iris_shuffle* const* streams; /* [3] (bg, voice, noise) or NULL */
+    float* d_features;        /* DEVICE, layout of cfg->feature_mode */
+    float* d_frame_labels;    /* DEVICE [B,T,K] or NULL (to_frame_labels, data_utils.py:64-70) */
+    float* d_labels_vtk;      /* DEVICE [B,V,T,K] or NULL (make_pipeline's label output) */
+    uint8_t* d_keep;          /* DEVICE [B,V] or NULL */
+    /* optional metric leg on this step's frame labels (metrics.py:217-298), enqueued on the
+     * context's own side stream right behind the labels kernel so that it runs beside the
+     * feature kernel: */
+    const float* d_y_pred;    /* DEVICE [B,T,K] model output, or NULL: no metric leg */
+    float threshold;          /* 0.5 */
+    int32_t* d_triples;       /* DEVICE [B,3] (n_true, n_pred, correct) of the local clips; with a
+                                 communicator: this rank's slice of a [B_global,3] send buffer whose
+                                 other rows stay zero (pass send + 3 * clip_lo) */
+    uint64_t* d_counts;       /* DEVICE [6] TP, FP, FN, sum n_true, sum n_pred, sum correct (accumulated) */
+    iris_nccl_comm comm;      /* not NULL: iris_allreduce_counts on the side stream after the counting */
+    int64_t* d_counts_reduced;   /* DEVICE [6] all-reduced copy of d_counts (with comm) */
+    const int32_t* d_triples_send;  /* DEVICE [B_global,3] (see d_triples) or NULL */
+    int32_t* d_triples_global;      /* DEVICE [B_global,3] all-reduced triples or NULL */
+    int32_t global_batch;
+} iris_step_io;
+
+/* One batch.  Everything is enqueued on `stream` (the metric leg on the context's side stream,
+ * ordered behind the labels kernel); returns when the launches are queued.  The host blocks only
+ * when it is more than four batches ahead of the device (ring of pinned plan buffers). */
+int iris_step(iris_ctx* ctx, const iris_step_config* cfg, const iris_step_io* io, iris_stream stream);
+/* Make `stream` wait for the metric leg (counts and their all-reduce) issued `lag` iris_step
+ * calls ago (0 = the latest).  The reduced counts are a logged metric (the reference reads them
+ * once per epoch, sj_train.py:454-462), so a training loop waits with lag >= 1 and the collective
+ * never stalls the feature kernels. */
+int iris_counts_wait(iris_ctx* ctx, int lag, iris_stream stream);
+/* The draws iris_step made for its last batch (host pointers owned by the context, valid until
+ * the next iris_step): what the parity oracle consumes. */
+int iris_step_draws(iris_ctx* ctx, iris_draws* out);
+
+/* The path's only exchange: NCCL sum over NVLink / NVSwitch of the int64 count
+ * vector [TP, FP, FN, sum n_true, sum n_pred, sum correct] and -- because the reference's ER is a
+ * mean of per-sample ratios clipped at the batch-global max(n_true) (metrics.py:268-273) -- of the
+ * per-sample triples: every rank fills its slice of a zero-initialised [B_global,3] int32 buffer
+ * (sum over disjoint slices == all-gather, ragged shards included).  Both reductions are one NCCL
+ * group on `stream`.  d_triples_* may be NULL.  NCCL is resolved at run time from the process
+ * (the library the framework already loaded) or from libnccl.so.2. */
+int iris_allreduce_counts(iris_ctx* ctx, iris_nccl_comm comm, const int64_t* d_counts_send,
+                          int64_t* d_counts_recv, const int32_t* d_triples_send,
+                          int32_t* d_triples_recv, int global_batch, iris_stream stream);
+/* Communicator plumbing for callers that do not own an ncclComm_t: rank 0 makes an id
+ * (128 bytes), every rank joins with it. */
+int iris_nccl_unique_id(void* out_id_128);
+int iris_nccl_comm_create(iris_ctx* ctx, const void* id_128, int rank, int world_size, iris_nccl_comm* out);
+int iris_nccl_comm_destroy(iris_nccl_comm comm);
+/* metrics.py:268-273 on already reduced triples [n,3] -> er [n] (the denominator clips at the
+ * batch-global max(n_true)). */
+int iris_er_from_triples(iris_ctx* ctx, const int32_t* d_triples, int n, float* d_er, iris_stream stream);
+
+/* Pinned host memory on the NUMA node of the context's GPU (mmap + mbind + cudaHostRegister):
+ * staging for the device -> host read-back of features on multi-socket boxes where every rank's
+ * default allocations land on one node.  *numa_node receives the node used (-1: not bound). */
+int iris_host_alloc(iris_ctx* ctx, size_t bytes, void** out, int* numa_node);
+int iris_host_free(iris_ctx* ctx, void* p, size_t bytes);
+
+/* ---- DLPack hand-over (the exchange format north_star names) ----
+ * `managed` points at a DLManagedTensor (dlpack.h ABI: the struct behind the "dltensor"
+ * capsule of torch.utils.dlpack.to_dlpack / tf.experimental.dlpack.to_dlpack).  The entry points
+ * check device, dtype (float32), contiguity and shape against the plan and then write through
+ * data + byte_offset: the tensor stays owned by the producing framework, nothing is copied. */
+int iris_features_dlpack(iris_ctx* ctx, int mode, void* managed, iris_stream stream);
+int iris_labels_dlpack(iris_ctx* ctx, void* managed_vtk, void* managed_frame, iris_stream stream);
+int iris_step_dlpack(iris_ctx* ctx, const iris_step_config* cfg, const double* uniforms,
+                     iris_shuffle* const* streams, void* managed_features, void* managed_frame_labels,
+                     iris_stream stream);
+/* Whether iris_set_mel's matrix runs in the fused epilogue (else: IRIS_FEAT_MAGPHASE +
+ * iris_op_mel), and the most mixing segments one clip may have in the fused kernel. */
+int iris_mel_fusable(iris_ctx* ctx);
+int iris_max_segments(void);
 
 #ifdef __cplusplus
 }

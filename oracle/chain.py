@@ -36,10 +36,14 @@ def clip_draws(d, b):
     if d.max_voices > 0:
         out['n_voices'] = int(d.n_voices[b])
         out['voice_u'] = d.voice_u[b]
+        if d.voice_gain is not None:    # the host's pow(10., -u) (libm powf in iris_draw_batch): a draw like the others
+            out['voice_gain'] = d.voice_gain[b]
         out['voice_offset'] = d.voice_offset[b]
     if d.max_noises > 0:
         out['n_noises'] = int(d.n_noises[b])
         out['noise_u'] = d.noise_u[b]
+        if d.noise_gain is not None:
+            out['noise_gain'] = d.noise_gain[b]
         out['noise_offset'] = d.noise_offset[b]
     return out
 

@@ -24,6 +24,8 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
       n_noises       int in [0, max_noises)                              (87-88)
       noise_u[n]     fp32 in [0, 2); gain = pow(10f, -u)                (94)
       noise_offset[n] int in [0, len - n_frame]  (random_crop)           (103)
+      voice_gain / noise_gain (optional): the host's fp32 ``pow(10., -u)`` handed over as a draw
+      (libm ``powf`` and numpy's ``power`` differ in the last bit for ~1 % of the inputs)
     """
     f32 = np.float32
     assert t_axis == 1
@@ -51,8 +53,11 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
     label = np.zeros([max_voices, n_frame, n_classes], f32)
     for v in range(n_voices):
         voice = voices[v]
-        u = f32(draws['voice_u'][v])
-        v_ratio = np.power(f32(10.), -u, dtype=f32)
+        if draws.get('voice_gain') is not None:   # the host's pow(10., -u), passed explicitly like every draw
+            v_ratio = f32(draws['voice_gain'][v])
+        else:
+            u = f32(draws['voice_u'][v])
+            v_ratio = np.power(f32(10.), -u, dtype=f32)
         v_frame = voice.shape[1]
 
         l = np.tile(labels[v:v + 1], [v_frame, 1])              # [v_frame, K]
@@ -89,8 +94,11 @@ def merge_complex_specs(background, voices_and_labels, noises=None, n_frame=300,
         assert 0 <= n_noises < max(noises.shape[0], 1) or n_noises == 0
         for n in range(n_noises):
             noise = noises[n]
-            u = f32(draws['noise_u'][n])
-            n_ratio = np.power(f32(10.), -u, dtype=f32)
+            if draws.get('noise_gain') is not None:
+                n_ratio = f32(draws['noise_gain'][n])
+            else:
+                u = f32(draws['noise_u'][n])
+                n_ratio = np.power(f32(10.), -u, dtype=f32)
             ns_frame = f32(noise.shape[1])
             pad_size = n_frame - int(np.int32(f32(min_noise_ratio) * ns_frame))
             if pad_size > 0:

@@ -29,7 +29,8 @@ def test_draw_ranges_follow_reference():
     assert np.all((d.n_voices >= 1) & (d.n_voices < V))                      # :43
     assert np.all((d.n_noises >= 0) & (d.n_noises < M))                      # :87
     assert np.all((d.voice_u >= 0) & (d.voice_u < 2)) and d.voice_u.dtype == np.float32
-    assert np.array_equal(d.voice_gain, np.power(np.float32(10), -d.voice_u, dtype=np.float32))
+    # gain = pow(10., -u) (pipeline.py:50) from libm's powf; numpy's float32 power may differ in the last bit
+    np.testing.assert_array_max_ulp(d.voice_gain, np.power(np.float32(10), -d.voice_u, dtype=np.float32), maxulp=1)
     for b in range(500):
         vP = vf[d.voice_id[b]].max()
         pad, length = placement(T, vP, 1)
@@ -72,6 +73,92 @@ def test_shuffle_stream_visits_everything():
     assert np.bincount(ids, minlength=10).min() > 60
 
 
+def _planner_case(rng, V, M, ntm, nfm, me, B=64, T=626, with_streams=False, min_ratio=1.0):
+    from challenge_b200.plan import ShuffleStream, draw_config, draws_from_uniforms, uniforms_per_clip
+    from oracle import plan as OP
+    bgf = rng.integers(30, 700, 9).astype(np.int32)
+    vf = rng.integers(T // 2 + 1 if min_ratio < 1 else 8, 250, 23).astype(np.int32)
+    nf = rng.integers(8, 250, 11).astype(np.int32)
+    cfg = draw_config(B, T, V, M, -20, min_ratio, 0.5, ntm, 24, nfm, 16, 257, me)
+    u = rng.random((B, uniforms_per_clip(cfg)))
+    st_c = st_p = None
+    if with_streams:
+        st_c = {'bg': ShuffleStream(len(bgf), rng), 'voice': ShuffleStream(len(vf), rng),
+                'noise': ShuffleStream(len(nf), rng, 5)}
+        st_p = {'bg': OP.ShuffleStreamPy(len(bgf)), 'voice': OP.ShuffleStreamPy(len(vf)),
+                'noise': OP.ShuffleStreamPy(len(nf), 5)}
+    d = draws_from_uniforms(cfg, u, bgf, vf if V else None, nf if M else None, st_c)
+    r = OP.draws_from_uniforms(u, T, bgf, vf, nf, V, M, -20, min_ratio, 0.5, ntm, 24, nfm, 16, 257, me, st_p)
+    return d, r
+
+
+@pytest.mark.parametrize('with_streams', [False, True])
+@pytest.mark.parametrize('V,M,ntm,nfm,me', [(7, 2, 6, 1, 0), (1, 1, 0, 0, 2), (0, 0, 2, 0, 0),
+                                             (4, 0, 0, 1, 3), (10, 6, 6, 1, 0), (2, 1, 1, 1, 1)])
+def test_c_planner_is_bit_identical_to_the_numpy_restatement(V, M, ntm, nfm, me, with_streams):
+    """iris_draw_batch (the planner iris_step runs) against oracle/plan.py on the same block of
+    uniforms: every integer draw and every fp32 exponent draw identical; the gains
+    pow(10., -u) (pipeline.py:50, 94) agree to the last bit or one ulp (libm vs numpy)."""
+    d, r = _planner_case(np.random.default_rng(100 * V + M), V, M, ntm, nfm, me, with_streams=with_streams)
+    assert set(r) <= {f for f in vars(d) if getattr(d, f) is not None}
+    for k, v in r.items():
+        a = getattr(d, k)
+        assert a.dtype == v.dtype and a.shape == v.shape, k
+        if k.endswith('_gain'):
+            np.testing.assert_array_max_ulp(a, v, maxulp=1)
+        else:
+            assert np.array_equal(a, v), k
+
+
+def test_planner_fuzz_edge_cases():
+    """hypothesis fuzz of the planner's edge cases: V = 1 (n_voices fixed at 1, pipeline.py:41-46),
+    M in {0, 1} (n_noises in [0, M) is always 0 for M = 1), backgrounds shorter than n_frame (tiled,
+    pipeline.py:29-35), uniforms at the ends of [0, 1)."""
+    from hypothesis import given, settings, strategies as st
+    from challenge_b200.plan import draw_config, draws_from_uniforms, uniforms_per_clip
+    from oracle import plan as OP
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 3), st.integers(0, 2), st.integers(20, 400), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([0.0, 0.5, 1.0 - 2.0 ** -53]))
+    def run(V, M, T, seed, edge):
+        rng = np.random.default_rng(seed)
+        bgf = rng.integers(5, 2 * T, 4).astype(np.int32)       # some shorter than T: tiled
+        vf = rng.integers(T + 1, 2 * T + 2, 6).astype(np.int32)  # min_ratio 1: len - T >= 1
+        nf = rng.integers(3, 2 * T, 5).astype(np.int32)
+        B = 5
+        cfg = draw_config(B, T, V, M, -20, 1.0, 0.5, 2, 24 if T > 24 else T, 1, 16, 257, 1)
+        u = rng.random((B, uniforms_per_clip(cfg)))
+        u[0, :] = edge
+        d = draws_from_uniforms(cfg, u, bgf, vf if V else None, nf if M else None)
+        r = OP.draws_from_uniforms(u, T, bgf, vf, nf, V, M, -20, 1.0, 0.5, 2, cfg.time_mask_max, 1, 16, 257, 1)
+        for k, v in r.items():
+            a = getattr(d, k)
+            if k.endswith('_gain'):
+                np.testing.assert_array_max_ulp(a, v, maxulp=1)
+            else:
+                assert np.array_equal(a, v), k
+        if V == 1:
+            assert np.all(d.n_voices == 1)
+        if M == 1:
+            assert np.all(d.n_noises == 0)
+        bgT = bgf[d.bg_id].astype(np.int64)
+        assert np.all(d.bg_offset <= bgT * ((T + bgT - 1) // bgT) - T)
+    run()
+
+
+def test_planner_raises_where_the_reference_raises():
+    """len == n_frame leaves the empty range [0, 0) for the voice offset: tf.random.uniform raises
+    (pipeline.py:68-69) -> IRIS_ERR_EMPTY_RANGE -> InvalidArgumentError."""
+    from challenge_b200.errors import InvalidArgumentError
+    from challenge_b200.plan import draw_config, draws_from_uniforms, uniforms_per_clip
+    cfg = draw_config(2, 100, 2, 0, -20, 1.0, 0.5)
+    u = np.random.default_rng(0).random((2, uniforms_per_clip(cfg)))
+    with pytest.raises(InvalidArgumentError):
+        draws_from_uniforms(cfg, u, np.array([100]), np.array([100, 50]))
+    draws_from_uniforms(cfg, u, np.array([100]), np.array([101, 50]))   # len - T = 1: fine
+
+
 def _header_symbols():
     text = open(os.path.join(ROOT, 'include', 'iris.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
@@ -87,7 +174,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in syms:
         assert hasattr(lib, name), 'libiris.so does not export %s' % name
         assert name in _lib.SIGNATURES, 'no ctypes signature for %s' % name
-    assert lib.iris_abi_version() == 1
+    assert lib.iris_abi_version() == 2
 
 
 def test_no_cpu_fallback():
