@@ -882,6 +882,8 @@ int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
 
 int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_stream stream) {
     if (!c || !d_out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(d_out) & 15)
+        return fail(IRIS_ERR_INVALID, "the feature buffer must be 16-byte aligned (vector stores)");
     if (select < IRIS_SELECT_ALL || select > IRIS_SELECT_BG_NOISE) return fail(IRIS_ERR_INVALID, "bad segment selection");
     if (select != IRIS_SELECT_ALL && mode != IRIS_FEAT_COMPLEX)
         return fail(IRIS_ERR_INVALID, "only_voice / only_noise are complex spectrograms (pipeline.py:37-38)");
