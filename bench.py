@@ -4,16 +4,18 @@
   python bench.py --gpus N --steps K --warmup W            # the CUDA path (libiris)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
 
-Workload (`config.workload`): BASELINE.json configs[1] -- synthetic 2-ch 16 kHz 10 s clips,
-background + voices + noise mixed at sampled gains, 6 time + 1 frequency mask, batch 256,
-n_fft 512 / hop 256 / 80 mel, min-max + log, frame labels -- on every GPU (weak scaling:
-each rank draws and produces its own 256-clip slice), followed by the integer F1 / error-rate
-counting of the frame labels against a synthetic prediction; for N > 1 the count vector is
-all-reduced over NCCL (the path's only exchange).
+Workload (`config.workload`).  N = 1: BASELINE.json configs[1] -- synthetic 2-ch 16 kHz 10 s
+clips, background + voices + noise mixed at sampled gains, 6 time + 1 frequency mask, batch 256,
+n_fft 512 / hop 256 / 80 mel, min-max + log, frame labels, then the integer F1 / error-rate
+counting of the frame labels against a synthetic prediction.  The same line carries
+`configs3_one_gpu`: configs[3]'s 8192-clip batch on this one GPU.  N > 1: BASELINE.json
+configs[3] -- that 8192-clip batch sharded 8192 / N per GPU, the counts (int64[6] + the
+[8192,3] per-sample triples) all-reduced over NCCL inside libiris (the path's only exchange).
 
-One step = one batch.  `value` is timed with CUDA events on the launching stream with the
-plan already resident (L2 flushed between steps); `e2e` goes through the public drop-in
-call with host draws in, pinned host features + labels out.
+One step = one batch = ONE C call (iris_step).  `value` is timed with CUDA events on the
+launching stream with the banks resident and the host uniforms drawn beforehand (L2 flushed
+between steps); `e2e` iterates the public drop-in chain (make_pipeline(...).map(...).batch(B)...)
+with host draws in and pinned host features + labels + counts out.
 """
 import argparse
 import json
@@ -39,27 +41,55 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(n_chan=2, batch=256, n_frame=626, max_voices=7, max_noises=2, snr=-20, min_ratio=1,
            n_mels=80, n_time_masks=6, n_freq_masks=1, n_bg=64, n_voice=256, n_noise=64,
-           seed=20202)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_fused<FM_MEL> launch of this workload,
-# from the committed ncu --set full capture (profiles/); below the algorithmic bytes because the
-# 175 MB of banks are shared by the 256 clips and partly stay in the 126 MB L2
-NCU_TRAFFIC_BYTES = 439142144
-NCU_TRAFFIC_SRC = 'profiles/r01_v10_fused_ncu_raw.txt (411.4 MB read + 27.8 MB written; the mel rows stay in L2 for k_logmel_post)'
+           seed=20202, global_batch_cfg3=8192)
 METRIC = 'augmented spectrogram clips/sec'
 UNIT = 'clips/s'
 
 
-def workload_config(n_gpus):
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_fused<FM_MEL> launch of the configs[1]
+    workload, read from the newest committed `ncu --set full` capture under profiles/ (below the
+    algorithmic bytes: the 175 MB of banks are shared by the clips and partly stay in the 126 MB
+    L2, and the mel rows stay in L2 for k_logmel_post)."""
+    import glob
+    import re
+    unit = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_fused_ncu_raw.txt')),
+                   key=lambda p: [int(x) for x in re.findall(r'\d+', os.path.basename(p))])
+    for path in reversed(files):
+        tot = {}
+        for line in open(path):
+            m = re.match(r'(dram__bytes_(?:read|write)\.sum)\s+([0-9.,]+)\s+(\w+)', line)
+            if m and m.group(3) in unit:
+                tot[m.group(1)] = float(m.group(2).replace(',', '')) * unit[m.group(3)]
+        if len(tot) == 2:
+            return int(sum(tot.values())), os.path.relpath(path, ROOT)
+    return None, 'no ncu capture under profiles/'
+
+
+def workload_config(n_gpus, per_gpu=None):
+    """N = 1: BASELINE configs[1] (the configuration the metric is quoted on; it fits one GPU).
+    N > 1: BASELINE configs[3]: the 8192-clip batch of the same workload sharded 8192 / N per GPU
+    (strong scaling) with the NCCL all-reduce of the F1 / ER counts."""
+    what = ('2-ch 16 kHz 10 s clips + noise mixing at random SNR + time/freq masking -> min-max '
+            'log-mel [B,80,626,2] + frame labels [B,626,3] + F1/ER counts')
+    if n_gpus == 1:
+        per_gpu = per_gpu or CFG['batch']
+        name = 'BASELINE configs[1] (batch %d on 1 B200): ' % per_gpu
+        glob_b = per_gpu
+    else:
+        glob_b = CFG['global_batch_cfg3']
+        per_gpu = per_gpu or glob_b // n_gpus
+        name = ('BASELINE configs[3] (batch %d sharded over %d B200 = %d clips per GPU, NCCL all-reduce of '
+                'the F1/ER counts + the [%d,3] per-sample triples): ' % (glob_b, n_gpus, per_gpu, glob_b))
     return {
-        'workload': 'BASELINE configs[1]: 2-ch 16 kHz 10 s clips + noise mixing at random SNR '
-                    '+ time/freq masking -> min-max log-mel [B,80,626,2] + frame labels '
-                    '[B,626,3] + F1/ER counts',
-        'batch_per_gpu': CFG['batch'], 'global_batch': CFG['batch'] * n_gpus,
+        'workload': name + what,
+        'batch_per_gpu': per_gpu, 'global_batch': glob_b,
         'n_fft': 512, 'hop': 256, 'n_mels': CFG['n_mels'], 'n_frame': CFG['n_frame'],
         'max_voices': CFG['max_voices'], 'max_noises': CFG['max_noises'],
-        'banks': '%d bg x 10 s, %d voices / %d noises 0.5-4 s (seed %d)' % (
+        'banks': '%d bg x 10 s, %d voices / %d noises 0.5-4 s (seed %d), replicated per GPU' % (
             CFG['n_bg'], CFG['n_voice'], CFG['n_noise'], CFG['seed']),
-        'parallelism': 'dp%d (batch sharded by clip, int64 count all-reduce only)' % n_gpus,
+        'parallelism': 'dp%d (batch sharded by clip; the only exchange is the count all-reduce)' % n_gpus,
         'l2': 'flushed between timed steps (256 MiB write); banks + outputs exceed L2',
     }
 
@@ -226,9 +256,14 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def thread_settings():
+    return ', '.join('%s=%s' % (k, os.environ.get(k)) for k in _THREAD_ENV[:3])
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores;
-    each step is a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores; each step
+    is a bounded sample of the same workload (clips are independent, so clips/s does not depend on
+    the batch they are drawn into)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -248,14 +283,19 @@ def run_reference_arm(args):
         pool.close()
     total = float(np.sum(times))
     value = per_step * args.steps / total
-    sample = ('%d clips per step on %d processes (1 torch thread each); per-source load_wav '
-              '(STFT) precomputed offline as in the reference' % (per_step, cores))
+    sample = ('%d clips per step on %d worker processes, one thread each (%s); per-source load_wav '
+              '(STFT) precomputed offline as in the reference' % (per_step, cores, thread_settings()))
+    cfg = workload_config(args.gpus)
+    cfg['clips_per_step'] = per_step
+    cfg['note'] = ('CPU arm: every step is a bounded sample of %d clips of the workload above (not the '
+                   'whole batch); compare clips/s, not ms_per_step' % per_step)
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak' if args.gpus == 1 else 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.gpus),
+        'config': cfg,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -265,237 +305,278 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------
+def drop_in_dataset(banks, B):
+    """The public drop-in call chain of sj_train.make_dataset (sj_train.py:92-130) on the GPU
+    pipeline: make_pipeline -> to_frame_labels -> augment -> batch -> complex_to_magphase ->
+    magphase_to_mel(80) -> minmax -> log_on_mel (lowered to one iris_step per batch)."""
+    from challenge_b200 import data_utils as D, transforms as TR
+    from challenge_b200.pipeline import make_pipeline
+    bgs, voices, labels, noises = banks
+    ds = make_pipeline(bgs, voices, labels, noises, n_frame=CFG['n_frame'], max_voices=CFG['max_voices'],
+                       max_noises=CFG['max_noises'], snr=CFG['snr'], min_ratio=CFG['min_ratio'])
+    return (ds.map(D.to_frame_labels).map(D.augment).batch(B).map(TR.complex_to_magphase)
+            .map(TR.magphase_to_mel(CFG['n_mels'])).map(D.minmax).map(D.log_on_mel))
+
+
 def run_gpu_arm(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from challenge_b200 import _lib as L
-    from challenge_b200.engine import Engine
-    from challenge_b200.plan import draw_batch
+    from challenge_b200 import _ops as O
+    from challenge_b200.plan import draw_config, uniforms_per_clip
     from challenge_b200.synth import synthetic_banks
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    from challenge_b200.dist import bind_to_gpu_numa
+    from challenge_b200.dist import bind_to_gpu_numa, shard_range
     numa_cores = bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    eng = Engine(local)
-    eng.set_mel(CFG['n_mels'])
-    bgs, voices, labels, noises = synthetic_banks(CFG['seed'], CFG['n_chan'], CFG['n_bg'],
-                                                  CFG['n_voice'], CFG['n_noise'])
-    bf = eng.register_bank(L.BANK_BG, bgs)
-    vf = eng.register_bank(L.BANK_VOICE, voices, labels=labels)
-    nf = eng.register_bank(L.BANK_NOISE, noises)
-    B, T, K = CFG['batch'], CFG['n_frame'], 3
+    banks = synthetic_banks(CFG['seed'], CFG['n_chan'], CFG['n_bg'], CFG['n_voice'], CFG['n_noise'])
+    T, K = CFG['n_frame'], 3
+    if world == 1:
+        B = Bg = args.batch or CFG['batch']   # --batch: experiments only (config.workload names it)
+        lo = 0
+    else:
+        Bg = CFG['global_batch_cfg3']
+        lo, hi = shard_range(Bg, world, rank)
+        B = hi - lo
+    O.set_seed(CFG['seed'] + 100 + rank)
+    ds = drop_in_dataset(banks, B)          # registers the banks on this pipeline's engine
+    eng = ds.engine
+    fused, _, _ = ds._prepare()             # sets the mel matrix; the step configuration below is the lowered chain
+    assert fused['mode'] == L.FEAT_LOGMEL_MINMAX
     rng = np.random.default_rng(CFG['seed'] + 100 + rank)
 
-    def draw():
-        return draw_batch(rng, B, T, bf, vf, nf, max_voices=CFG['max_voices'],
-                          max_noises=CFG['max_noises'], snr=CFG['snr'], min_ratio=CFG['min_ratio'],
-                          n_time_masks=CFG['n_time_masks'], n_freq_masks=CFG['n_freq_masks'])
+    comm = None
+    if world > 1:      # the communicator of the count all-reduce lives inside libiris
+        ids = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = eng.nccl_comm(ids[0], rank, world)
 
-    n_all = args.warmup + args.steps
-    feat = [torch.empty((B, CFG['n_mels'], T, CFG['n_chan']), device=dev) for _ in range(2)]
-    # stand-in for the model output the metric kernels score (fixed, generated once)
-    y_pred = torch.rand((B, T, K), device=dev)
+    def step_setup(b, b_global, b_lo):
+        cfg = draw_config(b, T, CFG['max_voices'], CFG['max_noises'], CFG['snr'], CFG['min_ratio'], 0.5,
+                          CFG['n_time_masks'], 24, CFG['n_freq_masks'], 16)
+        st = dict(scfg=eng.step_config(cfg, L.FEAT_LOGMEL_MINMAX), n_u=uniforms_per_clip(cfg), b=b,
+                  feat=[torch.empty((b, CFG['n_mels'], T, CFG['n_chan']), device=dev) for _ in range(2)],
+                  frame=[torch.empty((b, T, K), device=dev) for _ in range(2)],
+                  # stand-in for the model output the metric kernels score (fixed, generated once)
+                  y_pred=torch.rand((b, T, K), device=dev),
+                  counts=torch.zeros(6, dtype=torch.int64, device=dev),
+                  reduced=torch.zeros(6, dtype=torch.int64, device=dev),
+                  send=torch.zeros((b_global, 3), dtype=torch.int32, device=dev),
+                  glob=torch.zeros((b_global, 3), dtype=torch.int32, device=dev), b_global=b_global, lo=b_lo)
+        return st
+
+    def one_step(st, u, i):
+        """ONE C call (iris_step): draws -> plan upload -> labels -> {features || metric counts
+        (+ count all-reduce on the side stream)}."""
+        j = i & 1
+        eng.step(st['scfg'], u, out=st['feat'][j], frame=st['frame'][j], y_pred=st['y_pred'],
+                 triples=st['send'][st['lo']:st['lo'] + st['b']], counts=st['counts'], comm=comm,
+                 counts_reduced=st['reduced'] if comm is not None else None,
+                 triples_send=st['send'] if comm is not None else None,
+                 triples_global=st['glob'] if comm is not None else None, global_batch=st['b_global'])
+        return j
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # one int64 [TP, FP, FN, sum n_true, sum n_pred, sum correct] row per step: filled by
-    # k_metric_counts, all-reduced in place over NCCL (the path's only exchange)
-    n_e2e_all = 0 if args.no_e2e else args.steps + max(args.warmup, 3)
-    counts = torch.zeros((n_all + n_e2e_all + 1, 6), dtype=torch.int64, device=dev)
-    KERNELS = ['k_labels', 'k_tiles', 'k_fused<FM_MEL>', 'k_logmel_post', 'k_metric_counts']
+    LAG = 2          # the reduced counts are a logged metric: consumed two steps late (N > 1)
 
-    side = torch.cuda.Stream(device=dev)
-    ev_lab = torch.cuda.Event()
-    ev_met = [torch.cuda.Event() for _ in range(2)]
-    met_pending = [False, False]
+    def timed_loop(st, n_warm, n_steps, sampler=None):
+        us = [rng.random((st['b'], st['n_u'])) for _ in range(n_warm + n_steps)]
+        eng.profile(False)
+        for s in range(n_warm):
+            one_step(st, us[s], s)
+            eng.counts_wait(0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+        eng.profile(True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(n_steps)]
+        for s in range(n_steps):
+            flush.fill_(s & 0xff)                               # evict L2 (untimed)
+            ev[s][0].record()
+            one_step(st, us[n_warm + s], s)
+            # one GPU: the step ends when its counts are there.  Several ranks: the collective is also a
+            # rendezvous of the ranks, so a step only waits for the counts issued LAG steps earlier
+            # and the last ones are drained inside the timed region.
+            eng.counts_wait(0 if (world == 1 or s == n_steps - 1) else LAG)
+            ev[s][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+        fused_ms, n_fused = eng.profile_read()
+        eng.profile(False)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        _, _, keep = eng.labels()   # keep flags of the last plan -> algorithmic bytes (kept sources only)
+        keep = keep.cpu().numpy()
+        bi, bo = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep)
+        # the launch the roofline hook timed: the whole batch, or the first part of a split batch
+        k_clips = eng.profile_clips() or st['b']
+        ki, ko = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep, clips=(0, k_clips))
+        return dict(total_ms=total_ms, total_ms_max=float(t.item()), fused_ms=fused_ms, n_fused=n_fused,
+                    alg_bytes=bi + bo, kernel_bytes=ki + ko, kernel_clips=k_clips)
 
-    def device_step(i, out):
-        """labels -> {fused features  ||  metric counts (+ count all-reduce)}: the counting only
-        needs the frame labels, so it runs on a second stream beside the feature kernel.  On one
-        GPU the step ends when both are done.  With several ranks the count all-reduce is also a
-        rendezvous of the ranks, so a step waits for the collective of the step BEFORE it (the
-        reduced counts are consumed one step late, like a logged Keras metric); `drain_counts`
-        waits for the last one inside the timed region."""
-        main = torch.cuda.current_stream()
-        frame, _, _ = eng.labels(want_keep=False)
-        ev_lab.record(main)
-        j = i & 1
-        with torch.cuda.stream(side):
-            side.wait_event(ev_lab)
-            eng.metric_counts(frame, y_pred, counts=counts[i], want_er=False)
-            if world > 1:
-                dist.all_reduce(counts[i])                  # NCCL sum of the int64 count vector
-            ev_met[j].record(side)
-            met_pending[j] = True
-            frame.record_stream(side)
-        eng.features(L.FEAT_LOGMEL_MINMAX, out=out)
-        k = j if world == 1 else j ^ 1
-        if met_pending[k]:
-            main.wait_event(ev_met[k])
-            met_pending[k] = False
-        return frame, ev_met[j]
-
-    def drain_counts():
-        main = torch.cuda.current_stream()
-        for k in range(2):
-            if met_pending[k]:
-                main.wait_event(ev_met[k])
-                met_pending[k] = False
-
-    # ---- kernel-resident timing: plan already uploaded, CUDA events per step ----
-    plans = [draw() for _ in range(n_all)]
-    eng.profile(False)
-    for s in range(args.warmup):
-        eng.upload_plan(plans[s])
-        device_step(s, feat[0])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # ---- device-timed: inputs (banks) resident, the uniforms of every step drawn beforehand ----
+    st = step_setup(B, Bg, lo)
     sampler = ClockSampler(local)
-    sampler.start()
-    eng.profile(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    for s in range(args.steps):
-        eng.upload_plan(plans[args.warmup + s])
-        flush.fill_(s & 0xff)                               # evict L2 (untimed)
-        ev[s][0].record()
-        device_step(args.warmup + s, feat[0])
-        if s == args.steps - 1:
-            drain_counts()                                  # the last collective ends inside the timed region
-        ev[s][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(np.sum(step_ms))
-    fused_ms, n_fused = eng.profile_read()
-    eng.profile(False)
-    # algorithmic bytes of the last plan (kept sources only), as an average per step
-    _, _, keep = eng.labels()
-    bi, bo = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep.cpu().numpy())
-    alg_bytes = bi + bo
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * B * args.steps / (total_ms_max / 1e3)
+    r = timed_loop(st, args.warmup, args.steps, sampler)
+    value = Bg * args.steps / (r['total_ms_max'] / 1e3)
 
-    # ---- end to end through the public call: host draws in, pinned host tensors out; the
-    # device->host copies of step i overlap the kernels of step i+1 (two buffers, two streams) ----
-    h_feat = [torch.empty(feat[0].shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    h_lbl = [torch.empty((B, T, K), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    h_cnt = [torch.empty(6, dtype=torch.int64, pin_memory=True) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    done = [torch.cuda.Event() for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    h2d = d2h = 0
-
-    # host randomness (numpy, ~0.4 ms per 256-clip batch) is drawn one step ahead on a worker
-    # thread, like a tf.data prefetch(1): the draws of step i+1 overlap the launches of step i
-    from concurrent.futures import ThreadPoolExecutor
-    drawer = ThreadPoolExecutor(max_workers=1)
-    next_draw = [drawer.submit(draw)]
-
-    def e2e_step(i, features_to_host=True):
-        nonlocal h2d, d2h
-        j = i & 1
-        row = n_all + i
-        d = next_draw[0].result()                           # host randomness (numpy), drawn ahead
-        next_draw[0] = drawer.submit(draw)
-        torch.cuda.current_stream().wait_event(copied[j])   # buffer j is free again
-        info = eng.upload_plan(d)                           # H2D of the draws (pinned staging)
-        frame, counted = device_step(row, feat[j])
-        done[j].record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[j])
-            copy_stream.wait_event(counted)                 # this step's (all-reduced) counts
-            if features_to_host:
-                h_feat[j].copy_(feat[j], non_blocking=True)
-            h_lbl[j].copy_(frame, non_blocking=True)
-            h_cnt[j].copy_(counts[row], non_blocking=True)
-            copied[j].record()
-            frame.record_stream(copy_stream)
-        if features_to_host:
-            h2d = info['bytes']
-            d2h = h_feat[j].numel() * 4 + h_lbl[j].numel() * 4 + h_cnt[j].numel() * 8
-
+    # ---- end to end through the public drop-in call chain: host uniforms in (numpy) -> one iris_step
+    # per batch inside IrisDataset -> features + labels + counts copied to pinned host memory; the
+    # device->host copies of batch i overlap the kernels of batch i+1 (two buffers, two streams) ----
     n_e2e = 0 if args.no_e2e else args.steps
     n_e2e_warm = 0 if args.no_e2e else max(args.warmup, 3)
-    for i in range(n_e2e_warm):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        e2e_step(n_e2e_warm + i)
-    torch.cuda.synchronize()
-    e2e_s = max(time.perf_counter() - t0, 1e-9)
+    feat_shape = (B, CFG['n_mels'], T, CFG['n_chan'])
+    h2d = d2h = 0
+    e2e_value = e2e_dev_value = None
+    numa_node = None
+    if not args.no_e2e:
+        h_feat = []
+        for _ in range(2):      # pinned staging on the NUMA node of this rank's GPU
+            a, numa_node = eng.host_alloc(feat_shape, np.float32)
+            h_feat.append(torch.from_numpy(a))
+        h_lbl = [torch.empty((B, T, K), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        h_cnt = [torch.empty(6, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        e_counts = torch.zeros(6, dtype=torch.int64, device=dev)
+        e_reduced = torch.zeros(6, dtype=torch.int64, device=dev)
+        it = iter(ds)
+
+        def e2e_step(i, features_to_host=True):
+            nonlocal h2d, d2h
+            j = i & 1
+            x, y = next(it)                                     # host uniforms -> iris_step (public drop-in)
+            eng.metric_counts(y, st['y_pred'], counts=e_counts, want_er=False)
+            src_counts = e_counts
+            if comm is not None:
+                eng.allreduce_counts(comm, e_counts, e_reduced)
+                src_counts = e_reduced
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                if features_to_host:
+                    h_feat[j].copy_(x, non_blocking=True)
+                h_lbl[j].copy_(y, non_blocking=True)
+                h_cnt[j].copy_(src_counts, non_blocking=True)
+                copied[j].record()
+                x.record_stream(copy_stream)
+                y.record_stream(copy_stream)
+            copied[j ^ 1].synchronize()                         # the consumer has batch i-1 on the host
+            if features_to_host:
+                h2d = eng.plan_upload_bytes()   # the packed plan blob (segments, ids, masks) of this batch
+                d2h = h_feat[j].numel() * 4 + h_lbl[j].numel() * 4 + h_cnt[j].numel() * 8
+
+        def e2e_loop(n_warm, n, to_host):
+            for i in range(n_warm):
+                e2e_step(i, to_host)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(n):
+                e2e_step(n_warm + i, to_host)
+            torch.cuda.synchronize()
+            t = torch.tensor([max(time.perf_counter() - t0, 1e-9)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return Bg * n / float(t.item()), float(t.item())
+
+        e2e_value, e2e_s = e2e_loop(n_e2e_warm, n_e2e, True)
+        # the same loop with the features left on the device (what a Keras / torch model fed through
+        # DLPack sees: INTEGRATION.md section 3); labels and counts still go to the host
+        e2e_dev_value, _ = e2e_loop(2, n_e2e, False)
     clocks = sampler.stop()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * n_e2e / float(t.item())
-    # the same loop with the features left on the device (what a Keras / torch model fed through
-    # DLPack sees: INTEGRATION.md section 3); labels and counts still go to the host.  Context for
-    # the PCIe-bound number above, not the e2e value.
-    for i in range(min(n_e2e_warm, 2)):
-        e2e_step(i, features_to_host=False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        e2e_step(i, features_to_host=False)
-    torch.cuda.synchronize()
-    t = torch.tensor([max(time.perf_counter() - t0, 1e-9)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_dev_value = world * B * n_e2e / float(t.item())
-    next_draw[0].result()
-    drawer.shutdown()
+
+    # ---- N = 1: the multi-GPU configuration (configs[3], 8192 clips) on this one GPU, for the
+    # strong-scaling base of the N > 1 lines ----
+    cfg3 = None
+    if world == 1 and not args.no_cfg3:
+        st3 = step_setup(CFG['global_batch_cfg3'], CFG['global_batch_cfg3'], 0)
+        r3 = timed_loop(st3, 5, 4)     # 5 warm-up steps: every slot of the plan ring is allocated
+        cfg3 = {'workload': 'BASELINE configs[3] on ONE GPU: batch 8192 in one step (same per-clip workload)',
+                'value': 8192 * 4 / (r3['total_ms'] / 1e3), 'unit': UNIT, 'ms_per_step': r3['total_ms'] / 4,
+                'steps': 4, 'algorithmic_bytes_per_step': int(r3['alg_bytes']),
+                'step_frac': r3['alg_bytes'] * 4 / (r3['total_ms'] / 1e3) / 1e9 / measured_peak()[0]}
+        del st3
+        torch.cuda.empty_cache()
 
     peak, peak_src = measured_peak()
-    fused_avg_ms = fused_ms / max(n_fused, 1)
-    achieved = alg_bytes / (fused_avg_ms / 1e3) / 1e9 if fused_avg_ms > 0 else 0.0
+    fused_avg_ms = r['fused_ms'] / max(r['n_fused'], 1)
+    achieved = r['kernel_bytes'] / (fused_avg_ms / 1e3) / 1e9 if fused_avg_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic()
+    KERNELS = ['k_labels', 'k_tiles', 'k_fused<FM_MEL>', 'k_logmel_post', 'k_metric_counts']
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(world),
+        'warmup': args.warmup, 'ms_per_step': r['total_ms_max'] / args.steps,
+        'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, B),
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                'd2h_bytes_per_step': int(d2h),
-                'note': 'host draws (numpy, one step ahead on a worker thread) -> iris_plan_upload (H2D) -> kernels -> features + '
-                        'labels + counts copied to pinned host memory; wall clock; the D2H of '
-                        'step i overlaps the kernels of step i+1; PCIe-bound (features are '
-                        '400 KB per clip)',
-                'features_on_device_value': e2e_dev_value,
-                'features_on_device_note': 'same loop, features handed over on the device (DLPack) '
-                                           'instead of copied to the host; labels + counts still read back'},
         'kernels_per_step': KERNELS,
         'roofline': {'bound': 'hbm', 'kernel': 'k_fused<FM_MEL> (+ k_tiles)', 'achieved': achieved,
                      'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
-                     'traffic': NCU_TRAFFIC_BYTES, 'traffic_source': NCU_TRAFFIC_SRC,
+                     'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': int(alg_bytes),
-                     'kernel_ms': fused_avg_ms, 'kernel_share_of_step': fused_ms / total_ms},
+                     'algorithmic_bytes_per_launch': int(r['kernel_bytes']),
+                     'clips_per_launch': int(r['kernel_clips']),
+                     'launch_note': ('k_tiles + k_fused over the whole batch' if r['kernel_clips'] == B else
+                                     'the batch is split into parts of %d clips whose second pass (k_logmel_post) '
+                                     'overlaps the next part; the hook times k_tiles + k_fused of the first part'
+                                     % r['kernel_clips']),
+                     'algorithmic_bytes_per_step': int(r['alg_bytes']),
+                     'kernel_ms': fused_avg_ms,
+                     'kernel_share_of_step': (r['fused_ms'] * B / max(r['kernel_clips'], 1)) / r['total_ms'],
+                     'step_frac': r['alg_bytes'] * args.steps / (r['total_ms'] / 1e3) / 1e9 / peak},
+        'step_call': 'one iris_step C call per batch (host planner + plan upload + 5 kernel launches'
+                     + (' + 1 NCCL group' if world > 1 else '') + ')',
     }
+    if e2e_value is not None:
+        out['e2e'] = {
+            'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+            'd2h_gb_per_s_per_rank': d2h * n_e2e / e2e_s / 1e9,
+            'pinned_numa_node': numa_node,
+            'note': 'public drop-in chain (make_pipeline(...).map(to_frame_labels).map(augment).batch(B)'
+                    '.map(complex_to_magphase).map(magphase_to_mel(80)).map(minmax).map(log_on_mel)) iterated '
+                    'on the host: numpy uniforms -> one iris_step per batch -> metric counts -> features + '
+                    'labels + counts copied to pinned host memory (NUMA-local to the GPU); wall clock; the D2H '
+                    'of batch i overlaps the kernels of batch i+1; PCIe-bound (features are 400 KB per clip)',
+            'features_on_device_value': e2e_dev_value,
+            'features_on_device_note': 'same loop, features handed over on the device (DLPack) instead of '
+                                       'copied to the host; labels + counts still read back'}
+    if cfg3 is not None:
+        out['configs3_one_gpu'] = cfg3
     if world > 1:
         out['config']['host_binding'] = ('each rank pinned to the %d cores NVML lists for its GPU' % len(numa_cores)
                                          if numa_cores else 'none (NVML affinity not available)')
-        out['config']['count_allreduce'] = 'one NCCL all-reduce of int64[6] per step on a side stream; a step waits for the collective of the previous step, the last one is drained inside the timed region'
+        out['config']['count_allreduce'] = ('iris_allreduce_counts (NCCL inside libiris, one group of int64[6] + '
+                                            'int32[%d,3] per step) on the context side stream; a step waits for the '
+                                            'collective issued %d steps earlier, the last ones are drained inside the '
+                                            'timed region' % (Bg, LAG))
+        out['config']['efficiency_base'] = ('strong scaling of configs[3]: compare with configs3_one_gpu.value of the '
+                                            'N = 1 line (8192 clips on one GPU), not with its configs[1] value')
     out['gpu_launches'] = int(args.steps * (len(KERNELS) + (1 if world > 1 else 0)))
+    if comm is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        eng.nccl_comm_destroy(comm)
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:   # the CPU leg is timed at N = 1 only
+        if not args.no_cpu_baseline:      # the CPU leg, on rank 0's host cores, at every N
             out['cpu_baseline'] = cpu_baseline()
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -521,9 +602,9 @@ def cpu_baseline():
         pool.close()
     return {'value': n / wall, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'single_thread_value': n1 / t1,
-            'sample': '%d clips of the same workload on %d processes (1 torch thread each), '
+            'sample': '%d clips of the same workload on %d worker processes, one thread each (%s), '
                       'per-source load_wav (STFT) precomputed offline as in the reference; '
-                      'single_thread_value: %d clips on 1 thread' % (n, cores, n1)}
+                      'single_thread_value: %d clips on 1 thread' % (n, cores, thread_settings(), n1)}
 
 
 def main():
@@ -534,6 +615,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
+    ap.add_argument('--batch', type=int, default=0, help='N = 1 only: another batch size (experiments)')
+    ap.add_argument('--no-cfg3', action='store_true', help='skip the 8192-clip single-GPU leg (profiling runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

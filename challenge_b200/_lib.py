@@ -95,6 +95,9 @@ SIGNATURES = {
     'iris_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i32p, C.c_int]),
     'iris_plan_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
+    'iris_plan_bytes_clips': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'iris_profile_clips': (C.c_int, [C.c_void_p]),
     # stand-alone stages (include/iris.h, second half)
     'iris_op_mask': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                C.c_void_p, C.c_int, C.c_void_p]),
@@ -160,6 +163,7 @@ SIGNATURES = {
     'iris_step_dlpack': (C.c_int, [C.c_void_p, C.POINTER(IrisStepConfig), C.c_void_p, C.POINTER(C.c_void_p),
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'iris_mel_fusable': (C.c_int, [C.c_void_p]),
+    'iris_plan_upload_bytes': (C.c_int64, [C.c_void_p]),
     'iris_max_segments': (C.c_int, []),
 }
 PW_C2MP, PW_MP2C, PW_LOG_MAGPHASE, PW_LOG_ON_MEL, PW_MULTIPLY = range(5)

@@ -47,8 +47,8 @@ int build_tables(iris_ctx* c) {
     CU(cudaMemcpy(c->tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->ts.p, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->whalf.p, hann.data(), hann.size() * 4, cudaMemcpyHostToDevice));
-    CU(c->sched.reserve(16));
-    CU(cudaMemset(c->sched.p, 0, 16));
+    CU(c->sched.reserve(8 * 64));     // (next chunk, CTAs finished) per launch of a split batch
+    CU(cudaMemset(c->sched.p, 0, 8 * 64));
     return IRIS_OK;
 }
 
@@ -121,8 +121,8 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
     return IRIS_OK;
 }
 
-// tile-block scratch of a launch, then k_tiles + k_fused
-int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
+// tile-block scratch + launch parameters of a launch
+int prepare_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs) {
     p.max_segs = max_segs < 1 ? 1 : max_segs;
     p.stage_out = fused_stages_output(mode, p.remap, p.fr) && !getenv("IRIS_NO_STAGE") ? 1 : 0;
     p.fm_bits = (mode == FM_MEL && p.mel_f_lo + p.mel_f_n <= 128) ? 1 : 0;   // = the NJ == 4 kernels
@@ -140,26 +140,111 @@ int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t 
         if (v >= 1 && v <= 4096) p.chunk = v;
     }
     if (p.pair_merge && (p.chunk & 1)) ++p.chunk;   // both pairs of a (clip, time) range in one work claim
+    p.tile_first = 0;
+    p.tile_count = 0;
+    return IRIS_OK;
+}
+
+// k_tiles + k_fused over the whole batch
+int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
+    int rc = prepare_fused(c, p, mode, max_segs);
+    if (rc) return rc;
     CU(launch_fused(p, mode, c->num_sms, st));
     return IRIS_OK;
 }
 
-int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
-    if (!c->profile) return run_fused(c, p, mode, c->max_segs, st);
+int prof_events(iris_ctx* c, std::pair<cudaEvent_t, cudaEvent_t>** out) {
     if (c->prof_used == c->prof_events.size()) {
         cudaEvent_t a, b;
         CU(cudaEventCreate(&a));
         CU(cudaEventCreate(&b));
         c->prof_events.emplace_back(a, b);
     }
-    auto& ev = c->prof_events[c->prof_used++];
-    CU(cudaEventRecord(ev.first, st));
-    int rc = run_fused(c, p, mode, c->max_segs, st);
-    if (rc) return rc;
-    CU(cudaEventRecord(ev.second, st));
+    *out = &c->prof_events[c->prof_used++];
     return IRIS_OK;
 }
 
+int timed_fused(iris_ctx* c, FusedParams& p, int mode, cudaStream_t st) {
+    if (!c->profile) return run_fused(c, p, mode, c->max_segs, st);
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    int rc = prof_events(c, &ev);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev->first, st));
+    rc = run_fused(c, p, mode, c->max_segs, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev->second, st));
+    c->prof_clips = c->B;
+    return IRIS_OK;
+}
+
+// Clips per part of a split min-max log-mel launch (0: one launch).  k_logmel_post needs every
+// mel value of a clip, i.e. it can only follow k_fused; with the batch cut into parts that
+// alternate between two streams the second pass of part i runs beside k_fused of part i + 1
+// (one small CTA fits next to the two resident k_fused CTAs of an SM) and reads its rows out of
+// L2 even when the whole batch is far larger than L2.
+int split_part_clips(int B) {
+    // Experiment switch, off by default.  Measured on B200 (profiles/r02_split_ab.txt): every k_fused
+    // launch pays ~30 us of ramp-up and tail (t = 30 us + 0.62 us per clip), which is more than the
+    // overlap returns: batch 256 in two parts 239 -> 258 us, batch 1024 in four 855 -> 875 us,
+    // batch 8192 in 32 parts 6.68 -> 7.04 ms.
+    int part = 0;
+    if (const char* e = getenv("IRIS_SPLIT")) part = atoi(e);
+    if (part <= 0 || B < 2 * part) return 0;
+    const int max_parts = 64;   // work counters of c->sched
+    if ((B + part - 1) / part > max_parts) part = (B + max_parts - 1) / max_parts;
+    return part;
+}
+
+// min-max log-mel: k_tiles (whole batch) -> per part {k_fused -> k_logmel_post}
+int run_logmel_minmax(iris_ctx* c, FusedParams& p, float* d_out, cudaStream_t st) {
+    const size_t per_clip = size_t(c->n_mel) * c->T * c->C;
+    uint32_t* mm = c->minmax.as<uint32_t>();
+    unsigned* done = reinterpret_cast<unsigned*>(mm + 2 * size_t(c->B));
+    const int part = split_part_clips(c->B);
+    if (part == 0) {
+        int rc = timed_fused(c, p, FM_MEL, st);
+        if (rc) return rc;
+        CU(launch_logmel_post(d_out, mm, done, c->B, per_clip, 1, 1, st));
+        return IRIS_OK;
+    }
+    if (!c->aux) {
+        CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_tiles, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    int rc = prepare_fused(c, p, FM_MEL, c->max_segs);
+    if (rc) return rc;
+    const int per_clip_tiles = ((c->T + p.fr - 1) / p.fr) * p.n_pairs;
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    if (c->profile) {   // the roofline hook times k_tiles + k_fused of the first part
+        rc = prof_events(c, &ev);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev->first, st));
+    }
+    int n_parts = 0;
+    for (int b0 = 0; b0 < c->B; b0 += part, ++n_parts) {
+        const int nb = std::min(part, c->B - b0);
+        cudaStream_t s = (n_parts & 1) ? c->aux : st;
+        FusedParams q = p;
+        q.tile_first = b0 * per_clip_tiles;
+        q.tile_count = nb * per_clip_tiles;
+        q.sched = c->sched.as<uint32_t>() + 2 * n_parts;
+        CU(launch_fused(q, FM_MEL, c->num_sms, s, n_parts == 0 ? (FUSED_LAUNCH_TILES | FUSED_LAUNCH_KERNEL) : FUSED_LAUNCH_KERNEL));
+        if (n_parts == 0) {
+            if (ev) {
+                CU(cudaEventRecord(ev->second, st));
+                c->prof_clips = nb;
+            }
+            // the other stream starts behind k_tiles (and behind whatever the caller queued before)
+            CU(cudaEventRecord(c->ev_tiles, st));
+            CU(cudaStreamWaitEvent(c->aux, c->ev_tiles, 0));
+        }
+        CU(launch_logmel_post(d_out + size_t(b0) * per_clip, mm + 2 * size_t(b0), done + b0, nb, per_clip, 1, 1, s));
+    }
+    CU(cudaEventRecord(c->ev_join, c->aux));
+    CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    return IRIS_OK;
+}
 
 // Features from spectrogram banks: the mix + per-cell epilogue is one streaming kernel
 // (k_spec.cu), for the mel modes with the projection and the per-clip extrema fused in.
@@ -204,7 +289,9 @@ int spec_features(iris_ctx* c, int mode, int select, float* d_out, cudaStream_t 
         }
         CU(launch_specmix(p, FM_MEL, c->mel_dense.as<float>(), c->mel_lo.as<int32_t>(),
                           c->mel_len.as<int32_t>(), st));
-        if (p.do_minmax) CU(launch_logmel_post(d_out, c->minmax.as<uint32_t>(), c->B, per_clip, 1, 1, st));
+        if (p.do_minmax)
+            CU(launch_logmel_post(d_out, c->minmax.as<uint32_t>(), c->minmax.as<unsigned>() + 2 * size_t(c->B), c->B,
+                                  per_clip, 1, 1, st));
         return IRIS_OK;
     }
     // many channels: magnitudes through a scratch spectrogram, then the stand-alone kernels
@@ -217,7 +304,7 @@ int spec_features(iris_ctx* c, int mode, int select, float* d_out, cudaStream_t 
         int rc = iris_op_minmax(c, 0, d_out, d_out, c->B, int64_t(per_clip), 1, st);
         if (rc) return rc;
     }
-    if (mode != IRIS_FEAT_MEL) CU(launch_logmel_post(d_out, nullptr, c->B, per_clip, 0, 1, st));
+    if (mode != IRIS_FEAT_MEL) CU(launch_logmel_post(d_out, nullptr, nullptr, c->B, per_clip, 0, 1, st));
     return IRIS_OK;
 }
 
@@ -275,7 +362,15 @@ int iris_ctx_destroy(iris_ctx* c) {
     for (auto& b : c->banks) {
         b.padded.release(); b.activity.release(); b.labels.release(); b.d_n_frames.release();
     }
-    for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->plan_blob, &c->keep,
+    for (auto& pb : c->plan_blobs) pb.release();
+    if (c->copy) {
+        cudaStreamDestroy(c->copy);
+        for (int i = 0; i < iris_ctx::kStageRing; ++i) {
+            if (c->blob_ready[i]) cudaEventDestroy(c->blob_ready[i]);
+            if (c->blob_used[i]) cudaEventDestroy(c->blob_used[i]);
+        }
+    }
+    for (DevBuf* d : {&c->tw, &c->whalf, &c->mel_info, &c->mel_w, &c->keep,
                       &c->minmax, &c->scratch_labels, &c->stft_pad, &c->stft_small, &c->tiles, &c->ts, &c->sched,
                       &c->mel_dense, &c->mel_lo, &c->mel_len, &c->op_small, &c->minmax_ops, &c->eval_scratch, &c->spec_scratch})
         d->release();
@@ -284,6 +379,9 @@ int iris_ctx_destroy(iris_ctx* c) {
         if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
     }
     iris_step_release(c);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->ev_tiles) cudaEventDestroy(c->ev_tiles);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& ev : c->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete c;
     return IRIS_OK;
@@ -824,8 +922,25 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     if (c->h_stage[slot]) CU(cudaEventSynchronize(c->stage_free[slot]));   // the upload that used it has drained
     rc = ensure_stage(c, slot, total);
     if (rc) return rc;
-    if (total > c->plan_blob.cap) CU(cudaStreamSynchronize(st));   // kernels of earlier batches still read the old blob
-    CU(c->plan_blob.reserve(total));
+    // The blob travels on the context's copy stream into a ring of device blobs, so that the
+    // upload of batch i + 1 overlaps the kernels of batch i.  Slot reuse: blob_used[s] (recorded on
+    // the caller's stream at the NEXT upload) marks the end of every kernel that read blob s.
+    if (!c->copy) {
+        CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < iris_ctx::kStageRing; ++i) {
+            CU(cudaEventCreateWithFlags(&c->blob_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->blob_used[i], cudaEventDisableTiming));
+        }
+    }
+    const int prev = (slot + iris_ctx::kStageRing - 1) % iris_ctx::kStageRing;
+    CU(cudaEventRecord(c->blob_used[prev], st));
+    c->blob_used_valid[prev] = true;
+    DevBuf& blob = c->plan_blobs[slot];
+    if (c->blob_used_valid[slot]) {
+        if (total > blob.cap) CU(cudaEventSynchronize(c->blob_used[slot]));   // about to free it
+        else CU(cudaStreamWaitEvent(c->copy, c->blob_used[slot], 0));
+    }
+    CU(blob.reserve(total));
     char* h = static_cast<char*>(c->h_stage[slot]);
     memcpy(h + o_segs, c->h_segs.data(), c->h_segs.size() * sizeof(Seg));
     memcpy(h + o_ptr, c->h_seg_ptr.data(), size_t(B + 1) * 4);
@@ -843,9 +958,12 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
         float* sf = reinterpret_cast<float*>(h + o_msf);
         for (size_t i = 0; i < size_t(B) * n_extra; ++i) sf[i] = sqrtf(1.f - pl->merge_factor[i]);
     }
-    CU(cudaMemcpyAsync(c->plan_blob.p, h, total, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(c->stage_free[slot], st));
-    char* d = c->plan_blob.as<char>();
+    CU(cudaMemcpyAsync(blob.p, h, total, cudaMemcpyHostToDevice, c->copy));
+    CU(cudaEventRecord(c->stage_free[slot], c->copy));
+    CU(cudaEventRecord(c->blob_ready[slot], c->copy));
+    CU(cudaStreamWaitEvent(st, c->blob_ready[slot], 0));
+    c->last_upload_bytes = total;
+    char* d = blob.as<char>();
     c->d_segs = reinterpret_cast<Seg*>(d + o_segs);
     c->d_seg_ptr = reinterpret_cast<int32_t*>(d + o_ptr);
     c->d_n_voices = reinterpret_cast<int32_t*>(d + o_nv);
@@ -936,11 +1054,8 @@ int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_s
             if (c->minmax.p != before) CU(cudaMemsetAsync(c->minmax.p, 0, c->minmax.cap, st));
             p.minmax = c->minmax.as<uint32_t>();
         }
-        rc = timed_fused(c, p, FM_MEL, st);
+        rc = p.do_minmax ? run_logmel_minmax(c, p, d_out, st) : timed_fused(c, p, FM_MEL, st);
         if (rc) return rc;
-        if (p.do_minmax)
-            CU(launch_logmel_post(d_out, c->minmax.as<uint32_t>(), c->B,
-                                  size_t(c->n_mel) * c->T * c->C, 1, 1, st));
     } else {
         rc = timed_fused(c, p, mode, st);
     }
@@ -1033,9 +1148,17 @@ int iris_profile_read(iris_ctx* c, double* total_ms, int32_t* n_launches, int re
 
 int iris_plan_bytes(iris_ctx* c, int mode, const uint8_t* host_keep, int64_t* bytes_in,
                     int64_t* bytes_out) {
+    return iris_plan_bytes_clips(c, mode, host_keep, 0, c ? c->B : 0, bytes_in, bytes_out);
+}
+
+int iris_profile_clips(iris_ctx* c) { return c ? c->prof_clips : 0; }
+
+int iris_plan_bytes_clips(iris_ctx* c, int mode, const uint8_t* host_keep, int clip_lo, int clip_hi,
+                          int64_t* bytes_in, int64_t* bytes_out) {
     if (!c || !c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
+    if (clip_lo < 0 || clip_hi > c->B || clip_lo > clip_hi) return fail(IRIS_ERR_INVALID, "bad clip range");
     int64_t in = 0;
-    for (size_t i = 0; i < c->h_segs.size(); ++i) {
+    for (size_t i = size_t(c->h_seg_ptr[clip_lo]); i < size_t(c->h_seg_ptr[clip_hi]); ++i) {
         const Seg& s = c->h_segs[i];
         if (s.keep_idx >= 0 && host_keep && !host_keep[s.keep_idx]) continue;
         // frames [t_lo, t_hi) read the samples of rows t_lo+shift .. t_hi+shift once,
@@ -1050,8 +1173,8 @@ int iris_plan_bytes(iris_ctx* c, int mode, const uint8_t* host_keep, int64_t* by
         in += samples * 4 * c->C;
     }
     int64_t out;
-    if (mode >= IRIS_FEAT_MEL) out = int64_t(c->B) * c->n_mel * c->T * c->C * 4;
-    else out = int64_t(c->B) * kBins * c->T * 2 * c->c_out * 4;
+    if (mode >= IRIS_FEAT_MEL) out = int64_t(clip_hi - clip_lo) * c->n_mel * c->T * c->C * 4;
+    else out = int64_t(clip_hi - clip_lo) * kBins * c->T * 2 * c->c_out * 4;
     if (bytes_in) *bytes_in = in;
     if (bytes_out) *bytes_out = out;
     return IRIS_OK;

@@ -58,6 +58,7 @@ struct FusedParams {
     int32_t tile_stride;
     int32_t max_segs;            // most mixing segments any clip has
     int32_t chunk;               // consecutive tiles per work claim
+    int32_t tile_first, tile_count;   // tiles [tile_first, tile_first + tile_count) of the batch belong to this launch
     int32_t seg_select;          // 0: every segment; 1: voices only; 2: background + noises only
                                  // (only_voice / only_noise of pipeline.py:37-38, 82-83, 104-108)
     uint32_t* sched;             // [2] next chunk, CTAs finished; zero between launches

@@ -86,7 +86,7 @@ struct iris_ctx {
     std::vector<Seg> h_segs;
     std::vector<int64_t> h_seg_len;   // true samples per channel of each segment's source
     std::vector<int32_t> h_seg_ptr;
-    DevBuf plan_blob, keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
+    DevBuf keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
     DevBuf tiles, sched;
     int max_segs = 1;
     // pinned staging for the plan blob: a ring, so that the host can run up to kStageRing batches
@@ -96,6 +96,12 @@ struct iris_ctx {
     size_t h_stage_cap[kStageRing] = {0, 0, 0, 0};
     cudaEvent_t stage_free[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
     int stage_next = 0;
+    size_t last_upload_bytes = 0;
+    DevBuf plan_blobs[kStageRing];     // device side of the ring
+    cudaStream_t copy = nullptr;       // plan uploads
+    cudaEvent_t blob_ready[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t blob_used[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
+    bool blob_used_valid[kStageRing] = {false, false, false, false};
     // device views into plan_blob
     Seg* d_segs = nullptr;
     int32_t *d_seg_ptr = nullptr, *d_n_voices = nullptr, *d_voice_id = nullptr,
@@ -105,11 +111,16 @@ struct iris_ctx {
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    int prof_clips = 0;               // clips of the launch the hook timed last (a split batch: its first part)
     // stand-alone ops (iris_ops_abi.cu): dense mel matrix + column supports, small scratch
     DevBuf mel_dense, mel_lo, mel_len, op_small, minmax_ops, eval_scratch, spec_scratch;
     bool spec_mode = false;            // the uploaded plan mixes spectrogram banks
     int mel_bins = 0;
     bool mel_fusable = false;
+    // split feature launches (iris_abi.cu): parts of a large batch alternate between the caller's
+    // stream and `aux`, so that k_logmel_post of one part runs beside k_fused of the next
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_tiles = nullptr, ev_join = nullptr;
     // ---- one-call step (iris_step.cu) ----
     cudaStream_t side = nullptr;       // metric leg: counting + count all-reduce beside the feature kernel
     cudaEvent_t ev_labels = nullptr;   // labels of the current step are written

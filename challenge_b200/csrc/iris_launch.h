@@ -7,7 +7,9 @@ namespace iris {
 
 struct FusedParams;
 
-cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream);
+enum { FUSED_LAUNCH_TILES = 1, FUSED_LAUNCH_KERNEL = 2 };
+cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream,
+                         int what = FUSED_LAUNCH_TILES | FUSED_LAUNCH_KERNEL);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
 int fused_max_segments();      // mixing segments one clip may have
 bool fused_stages_output(int mode, int remap, int fr);   // FusedParams::stage_out for a launch
@@ -18,7 +20,8 @@ int fused_pick_fr(int T, int mel_taps);   // frames per tile (consumer warps per
 size_t fused_tile_bytes(const FusedParams& p, int* stride_out);   // size of p.tile_blocks
 
 // k_post.cu
-cudaError_t launch_logmel_post(float* x, uint32_t* minmax, int B, size_t per_clip, int do_minmax,
+// minmax: [B,2] extrema words of the clips at x; done: [B] zeroed counters (both may be null without do_minmax)
+cudaError_t launch_logmel_post(float* x, uint32_t* minmax, unsigned* done, int B, size_t per_clip, int do_minmax,
                                int do_log, cudaStream_t stream);
 
 // k_bank.cu

@@ -591,6 +591,7 @@ int iris_step_dlpack(iris_ctx* c, const iris_step_config* cfg, const double* uni
     return iris_step(c, cfg, &io, stream);
 }
 
+int64_t iris_plan_upload_bytes(iris_ctx* c) { return c ? int64_t(c->last_upload_bytes) : 0; }
 int iris_mel_fusable(iris_ctx* c) { return c && c->mel_fusable ? 1 : 0; }
 int iris_max_segments(void) { return fused_max_segments(); }
 

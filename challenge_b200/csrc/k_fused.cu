@@ -277,7 +277,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const int mel_taps = kFix ? (fixed_mel_L(0) + fixed_mel_L(1) + fixed_mel_L(2)) : p.mel_taps;
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
     uint64_t* empty = reinterpret_cast<uint64_t*>(sm + OFF_EMPTY);
-    const int n_tiles = p.B * ((p.T + FR - 1) / FR) * p.n_pairs;
+    const int n_tiles = p.tile_count;   // of this launch (a batch may be split over several launches)
     const uint32_t slotB = slot_bytes(FR);
     unsigned char* slots = sm + off_slots(mel_taps, FR);
 
@@ -336,7 +336,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             if (lane == 0) next = atomicAdd(&p.sched[0], 1u);
             const int last = int(min((long long)n_tiles, first + CH));
             for (int tile = int(first); tile < last; ++tile, ++i) {
-                const unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
+                const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
                 unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
                 int4 c = make_int4(0, 0, 0, 0);
                 if (lane < chunks16) {
@@ -755,20 +755,29 @@ size_t fused_tile_bytes(const FusedParams& p, int* stride_out) {
     return size_t(n_tiles) * size_t(stride);
 }
 
-// p.tile_blocks (fused_tile_bytes) is provided by the caller.
-cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream) {
+// p.tile_blocks (fused_tile_bytes) is provided by the caller.  what: FUSED_LAUNCH_TILES builds the tile
+// blocks of the whole batch (k_tiles), FUSED_LAUNCH_KERNEL runs k_fused on the tiles
+// [p.tile_first, p.tile_first + p.tile_count) (tile_count 0: all of them).
+cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStream_t stream, int what) {
+    FusedParams p = p_in;
     const int FR = p.fr;
     if (FR < 1 || FR > kMaxFR) return cudaErrorInvalidValue;
     const int tpc = (p.T + FR - 1) / FR;
-    const long long n_tiles = (long long)p.B * p.n_pairs * tpc;
-    if (n_tiles <= 0) return cudaSuccess;
-    if (n_tiles > 0x7fffffffLL || p.max_segs > kMaxStages || p.n_pairs > 127) return cudaErrorInvalidValue;
+    const long long all_tiles = (long long)p.B * p.n_pairs * tpc;
+    if (all_tiles <= 0) return cudaSuccess;
+    if (p.tile_count == 0) { p.tile_first = 0; p.tile_count = int32_t(all_tiles); }
+    const long long n_tiles = p.tile_count;
+    if (p.tile_first < 0 || p.tile_first + n_tiles > all_tiles) return cudaErrorInvalidValue;
+    if (all_tiles > 0x7fffffffLL || p.max_segs > kMaxStages || p.n_pairs > 127) return cudaErrorInvalidValue;
     if (mode == FM_MEL && (long long)p.n_mel * p.T * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;   // 32-bit row offsets inside a clip
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    k_tiles<<<unsigned((n_tiles + 127) / 128), 128, 0, stream>>>(p);
+    if (what & FUSED_LAUNCH_TILES) k_tiles<<<unsigned((all_tiles + 127) / 128), 128, 0, stream>>>(p);
+    if (!(what & FUSED_LAUNCH_KERNEL)) return cudaGetLastError();
     const int threads = (FR + 1) * 32;
-    const int pdl = getenv("IRIS_NO_PDL") ? 0 : 1;
+    // programmatic dependent launch behind k_tiles of the same call (prologue overlap); a launch on
+    // its own (later part of a split batch) is an ordinary one
+    const int pdl = (what & FUSED_LAUNCH_TILES) && !getenv("IRIS_NO_PDL") ? 1 : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     // persistent grid: as many CTAs as are resident at once, asked of the occupancy calculator once

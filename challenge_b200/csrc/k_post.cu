@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(kPostThreads) k_logmel_post(float* __restrict_
     }
 }
 
-// minmax: [B,2] words followed by [B] zeroed counters (3 words per clip in total)
-cudaError_t launch_logmel_post(float* x, uint32_t* minmax, int B, size_t per_clip, int do_minmax,
+cudaError_t launch_logmel_post(float* x, uint32_t* minmax, unsigned* done, int B, size_t per_clip, int do_minmax,
                                int do_log, cudaStream_t stream) {
     if (B <= 0 || per_clip == 0 || (!do_minmax && !do_log)) return cudaSuccess;
     for (int b0 = 0; b0 < B; b0 += 65535) {
@@ -92,7 +91,7 @@ cudaError_t launch_logmel_post(float* x, uint32_t* minmax, int B, size_t per_cli
         cudaError_t e = cudaLaunchKernelEx(&cfg, k_logmel_post, x + size_t(b0) * per_clip,
                                            minmax ? minmax + 2 * size_t(b0) : static_cast<uint32_t*>(nullptr), per_clip,
                                            do_minmax, do_log,
-                                           minmax ? minmax + 2 * size_t(B) + b0 : static_cast<unsigned*>(nullptr));
+                                           done ? done + b0 : static_cast<unsigned*>(nullptr));
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();

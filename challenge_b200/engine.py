@@ -312,6 +312,9 @@ class Engine:
             d.merge_factor = arr('merge_factor', (B, g.merge_extra))
         return d
 
+    def plan_upload_bytes(self):
+        return int(self.lib.iris_plan_upload_bytes(self._ctx))
+
     def mel_fusable(self):
         return bool(self.lib.iris_mel_fusable(self._ctx))
 
@@ -371,13 +374,18 @@ class Engine:
         self._host_allocs.append((p, n))
         return a, node.value
 
-    def plan_bytes(self, mode, keep=None):
+    def plan_bytes(self, mode, keep=None, clips=None):
+        """Algorithmic bytes (in, out) of the uploaded plan, optionally of the clips ``[lo, hi)``."""
         bi, bo = C.c_int64(), C.c_int64()
         k = None if keep is None else np.ascontiguousarray(keep, np.uint8)
-        L.check(self.lib.iris_plan_bytes(self._ctx, int(mode),
-                                         k.ctypes.data if k is not None else None,
-                                         C.byref(bi), C.byref(bo)))
+        lo, hi = clips if clips is not None else (0, self._plan['B'])
+        L.check(self.lib.iris_plan_bytes_clips(self._ctx, int(mode),
+                                               k.ctypes.data if k is not None else None, int(lo), int(hi),
+                                               C.byref(bi), C.byref(bo)))
         return bi.value, bo.value
+
+    def profile_clips(self):
+        return int(self.lib.iris_profile_clips(self._ctx))
 
     def profile(self, enable=True):
         L.check(self.lib.iris_profile_enable(self._ctx, int(bool(enable))))

@@ -171,12 +171,19 @@ int iris_er_counts_pooled(iris_ctx* ctx, const float* d_y_true, int n_frame, con
  * every kept source frame range read + output elements); used by bench.py's roofline. */
 int iris_plan_bytes(iris_ctx* ctx, int mode, const uint8_t* host_keep, int64_t* bytes_in,
                     int64_t* bytes_out);
+/* The same for the clips [clip_lo, clip_hi) of the plan. */
+int iris_plan_bytes_clips(iris_ctx* ctx, int mode, const uint8_t* host_keep, int clip_lo, int clip_hi,
+                          int64_t* bytes_in, int64_t* bytes_out);
 
 /* Measurement hook for bench.py's roofline: when enabled, every launch of the fused
  * feature kernel inside iris_features() is bracketed by cudaEvents on the launching stream;
  * iris_profile_read() synchronises them and returns the summed device time. */
 int iris_profile_enable(iris_ctx* ctx, int enable);
 int iris_profile_read(iris_ctx* ctx, double* total_ms, int32_t* n_launches, int reset);
+/* Clips of the launch the hook timed last: the whole batch, or -- when a large min-max log-mel
+ * batch is split into parts whose second pass overlaps the next part's feature kernel -- the
+ * first part (the one launch whose start and end are not entangled with another kernel). */
+int iris_profile_clips(iris_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------
  * Stand-alone stages: the reference's public functions applied one at a time (what a
@@ -439,6 +446,8 @@ int iris_step_dlpack(iris_ctx* ctx, const iris_step_config* cfg, const double* u
 /* Whether iris_set_mel's matrix runs in the fused epilogue (else: IRIS_FEAT_MAGPHASE +
  * iris_op_mel), and the most mixing segments one clip may have in the fused kernel. */
 int iris_mel_fusable(iris_ctx* ctx);
+/* Bytes of the last plan blob copied host -> device (iris_plan_upload / iris_step). */
+int64_t iris_plan_upload_bytes(iris_ctx* ctx);
 int iris_max_segments(void);
 
 #ifdef __cplusplus

@@ -37,7 +37,7 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     comm = eng.nccl_comm(ids[0], rank, world)
 
-    Bg, T = 37, 200                           # ragged shards: 19 + 18
+    Bg, T = 37, 300                           # ragged shards: 19 + 18; T above the longest voice (251 frames)
     lo, hi = shard_range(Bg, world, rank)
     b = hi - lo
     cfg = draw_config(b, T, 5, 2, -20, 1.0, 0.5, 6, 24, 1, 16)
