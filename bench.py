@@ -163,52 +163,41 @@ def measured_peak():
 _CPU = {}
 
 
-def _cpu_init(seed):
+def _cpu_prepare(seed):
+    """Once, in the parent, before the worker processes are forked: the synthetic banks and
+    load_wav (STFT) of every source -- the reference does this offline and keeps the result as
+    its pickled banks (utils.load_data), so it is outside the timed region; the workers inherit
+    the arrays copy-on-write."""
+    if _CPU.get('seed') == seed:
+        return
     import torch
     torch.set_num_threads(1)
     from challenge_b200.synth import synthetic_banks
-    _CPU['raw'] = synthetic_banks(seed, CFG['n_chan'], CFG['n_bg'], CFG['n_voice'], CFG['n_noise'])
-    _CPU['spec'] = ({}, {}, {})
+    from oracle.data_utils import load_wav_array
+    raw = synthetic_banks(seed, CFG['n_chan'], CFG['n_bg'], CFG['n_voice'], CFG['n_noise'])
+    _CPU['raw'] = raw
+    _CPU['spec'] = tuple([load_wav_array(w) for w in raw[k]] for k in (0, 1, 3))
+    _CPU['seed'] = seed
 
 
-class _LazyBank:
-    """load_wav of a source on first use (the reference does this offline; excluded from
-    the timed region by warming the cache before timing)."""
-
-    def __init__(self, kind):
-        self.kind = kind
-
-    def __getitem__(self, i):
-        from oracle.data_utils import load_wav_array
-        cache = _CPU['spec'][self.kind]
-        if i not in cache:
-            raw = _CPU['raw'][(0, 1, 3)[self.kind]]
-            cache[i] = load_wav_array(raw[i])
-        return cache[i]
+def _cpu_worker_init():
+    import torch
+    torch.set_num_threads(1)
 
 
 def _cpu_clips(args):
-    """Run the reference chain for clips [lo, hi) of draws d; returns seconds (timed part)."""
-    d, lo, hi, warm = args
+    """The reference chain for clips [lo, hi) of draws d."""
+    d, lo, hi = args
     from oracle import chain
-    banks = (_LazyBank(0), _LazyBank(1), _LazyBank(2))
-    if warm:   # offline part: STFT of every source these clips touch
-        for b in range(lo, hi):
-            banks[0][int(d.bg_id[b])]
-            for i in d.voice_id[b]:
-                banks[1][int(i)]
-            for i in d.noise_id[b]:
-                banks[2][int(i)]
-        return 0.0
-    t0 = time.perf_counter()
+    from oracle import metrics as M
+    banks = _CPU['spec']
     x, y, _, _ = chain.dataset_batch(banks[0], banks[1], _CPU['raw'][2], banks[2], d,
                                      mode='logmel_minmax', n_mels=CFG['n_mels'],
                                      clips=range(lo, hi))
-    from oracle import metrics as M
     yp = np.clip(y + 0.25, 0, 1).astype(np.float32)
     M.er_parts(y, yp)
     M.f1_counts(y, yp)
-    return time.perf_counter() - t0
+    return hi - lo
 
 
 def cpu_draws(n_clips, seed):
@@ -223,25 +212,25 @@ def cpu_draws(n_clips, seed):
 
 
 class CpuPool:
-    """All host cores, one process per core over clips (fork; banks shared copy-on-write)."""
+    """All host cores: one single-threaded worker process per core (fork; banks shared
+    copy-on-write), clips handed out two at a time as workers become free."""
 
     def __init__(self, cores):
         import multiprocessing as mp
         self.cores = cores
-        _cpu_init(CFG['seed'])
-        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init,
-                                                initargs=(CFG['seed'],)) if cores > 1 else None
+        _cpu_prepare(CFG['seed'])
+        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_worker_init) if cores > 1 else None
 
-    def run(self, d, n_clips, warm=False):
+    def run(self, d, n_clips):
         """Wall seconds for n_clips clips of d spread over the cores."""
-        per = -(-n_clips // self.cores)
-        chunks = [(d, lo, min(lo + per, n_clips), warm) for lo in range(0, n_clips, per)]
+        chunks = [(d, lo, min(lo + 2, n_clips)) for lo in range(0, n_clips, 2)]
         t0 = time.perf_counter()
         if self.pool is None:
             for c in chunks:
                 _cpu_clips(c)
         else:
-            self.pool.map(_cpu_clips, chunks)
+            for _ in self.pool.imap_unordered(_cpu_clips, chunks):
+                pass
         return time.perf_counter() - t0
 
     def close(self):
@@ -268,11 +257,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = max(2 * cores, 8)
+    per_step = max(4 * cores, 16)
     pool = CpuPool(cores)
     try:
         d = cpu_draws(per_step * (args.steps + args.warmup), CFG['seed'] + 1)
-        pool.run(d, d.batch, warm=True)
         times = []
         for s in range(args.warmup + args.steps):
             ds = d.slice(s * per_step, (s + 1) * per_step)
@@ -502,6 +490,19 @@ def run_gpu_arm(args):
         # the same loop with the features left on the device (what a Keras / torch model fed through
         # DLPack sees: INTEGRATION.md section 3); labels and counts still go to the host
         e2e_dev_value, _ = e2e_loop(2, n_e2e, False)
+        # the ceiling of the read-back: every rank copies a feature batch device -> pinned host,
+        # nothing else running, all ranks at once
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(8):
+            h_feat[i & 1].copy_(st['feat'][i & 1], non_blocking=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        d2h_ceiling = 8 * h_feat[0].numel() * 4 / float(t.item()) / 1e9
     clocks = sampler.stop()
 
     # ---- N = 1: the multi-GPU configuration (configs[3], 8192 clips) on this one GPU, for the
@@ -550,6 +551,9 @@ def run_gpu_arm(args):
         out['e2e'] = {
             'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
             'd2h_gb_per_s_per_rank': d2h * n_e2e / e2e_s / 1e9,
+            'd2h_ceiling_gb_per_s_per_rank': d2h_ceiling,
+            'd2h_ceiling_note': 'plain cudaMemcpyAsync of the feature batch to the same pinned buffers, all ranks at '
+                                'once, nothing else running: what the host fabric of this box gives',
             'pinned_numa_node': numa_node,
             'note': 'public drop-in chain (make_pipeline(...).map(to_frame_labels).map(augment).batch(B)'
                     '.map(complex_to_magphase).map(magphase_to_mel(80)).map(minmax).map(log_on_mel)) iterated '
@@ -588,15 +592,15 @@ def cpu_baseline():
     """The oracle port of the reference pipeline timed on this box's host cores on a bounded
     sample of the same workload (reported beside the GPU number; not the target)."""
     cores = host_cores()
-    n = max(4 * cores, 16)
+    n = max(16 * cores, 64)         # ~10-15 s of CPU work
     pool = CpuPool(cores)
     try:
         d = cpu_draws(n, CFG['seed'] + 2)
-        pool.run(d, n, warm=True)
+        pool.run(d.slice(0, 2 * cores), 2 * cores)          # warm the workers (imports, first touches)
         wall = pool.run(d, n)
         one = CpuPool(1)
-        n1 = 8
-        one.run(d.slice(0, n1), n1, warm=True)
+        n1 = 16
+        one.run(d.slice(0, 2), 2)
         t1 = one.run(d.slice(0, n1), n1)
     finally:
         pool.close()
