@@ -87,8 +87,15 @@ int ensure_stage(iris_ctx* c, int slot, size_t bytes) {
     return IRIS_OK;
 }
 
-int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, cudaStream_t st) {
+int feature_params(iris_ctx* c, int mode, int select, FusedParams& p);
+bool tile_sig_matches(const iris_ctx* c, const FusedParams& p);
+void tile_sig_set(iris_ctx* c, const FusedParams& p);
+
+// feat_hint: feature mode of the launch that will follow (-1: unknown).  With a hint the label
+// kernel also builds the tile blocks of that launch (k_labels.cu), which then skips k_tiles.
+int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, cudaStream_t st, int feat_hint = -1) {
     const Bank& vb = c->banks[IRIS_BANK_VOICE];
+    c->tile_sig.valid = false;
     const int K = vb.ready ? vb.n_classes : 0;
     if (c->V > 0 && !vb.ready) return fail(IRIS_ERR_STATE, "voice bank not registered");
     CU(c->keep.reserve(size_t(c->B) * (c->V > 0 ? c->V : 1)));
@@ -114,7 +121,16 @@ int run_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep_out, c
     lp.labels_vtk = d_vtk;
     lp.frame_labels = frame;
     lp.keep = c->keep.as<uint8_t>();
-    CU(launch_labels(lp, st));
+    FusedParams fp;
+    bool tiles = false;
+    if (feat_hint >= IRIS_FEAT_COMPLEX && feat_hint <= IRIS_FEAT_LOGMEL_MINMAX && !c->spec_mode &&
+        !getenv("IRIS_NO_LABEL_TILES")) {
+        const bool mel = feat_hint >= IRIS_FEAT_MEL;
+        if (!(mel && (c->n_mel == 0 || !c->mel_fusable || c->remap != IRIS_REMAP_NONE)))
+            tiles = feature_params(c, feat_hint, IRIS_SELECT_ALL, fp) == IRIS_OK;
+    }
+    CU(launch_labels(lp, st, tiles ? &fp : nullptr));
+    if (tiles) tile_sig_set(c, fp);
     if (d_keep_out)
         CU(cudaMemcpyAsync(d_keep_out, c->keep.p, size_t(c->B) * c->V, cudaMemcpyDeviceToDevice, st));
     c->labels_done = true;
@@ -130,7 +146,9 @@ int prepare_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs) {
     p.l2_hints = getenv("IRIS_NO_L2_HINTS") ? 0 : 1;   // measured: min-max log-mel 255 -> 250 us
     int stride = 0;
     const size_t bytes = fused_tile_bytes(p, &stride);
+    const void* before = c->tiles.p;
     CU(c->tiles.reserve(bytes));
+    if (c->tiles.p != before) c->tile_sig.valid = false;
     p.tile_blocks = c->tiles.as<unsigned char>();
     p.tile_stride = stride;
     p.sched = c->sched.as<uint32_t>();
@@ -146,10 +164,35 @@ int prepare_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs) {
 }
 
 // k_tiles + k_fused over the whole batch
+bool tile_sig_matches(const iris_ctx* c, const FusedParams& p) {
+    const iris_ctx::TileSig& g = c->tile_sig;
+    return g.valid && g.segs == p.segs && g.keep == p.keep && g.B == p.B && g.T == p.T && g.fm_bits == p.fm_bits && g.seg_select == p.seg_select && g.fr == p.fr &&
+           g.n_pairs == p.n_pairs && g.max_segs == p.max_segs && g.stride == p.tile_stride &&
+           g.masks == ((p.tmask ? 1 : 0) | (p.fmask ? 2 : 0)) && g.filter_k == p.filter_k;
+}
+void tile_sig_set(iris_ctx* c, const FusedParams& p) {
+    iris_ctx::TileSig& g = c->tile_sig;
+    g.valid = true;
+    g.segs = p.segs; g.keep = p.keep; g.B = p.B; g.T = p.T;
+    g.fm_bits = p.fm_bits; g.seg_select = p.seg_select; g.fr = p.fr; g.n_pairs = p.n_pairs;
+    g.max_segs = p.max_segs; g.stride = p.tile_stride;
+    g.masks = (p.tmask ? 1 : 0) | (p.fmask ? 2 : 0);
+    g.filter_k = p.filter_k;
+}
+
+// k_tiles + k_fused over the whole batch; k_tiles is skipped when the tile blocks of this plan
+// already exist in this layout (built by k_labels or by an earlier feature launch)
 int run_fused(iris_ctx* c, FusedParams& p, int mode, int max_segs, cudaStream_t st) {
     int rc = prepare_fused(c, p, mode, max_segs);
     if (rc) return rc;
-    CU(launch_fused(p, mode, c->num_sms, st));
+    const bool have = tile_sig_matches(c, p);
+    CU(launch_fused(p, mode, c->num_sms, st,
+                    have ? (FUSED_LAUNCH_KERNEL | FUSED_LAUNCH_PDL) : (FUSED_LAUNCH_TILES | FUSED_LAUNCH_KERNEL)));
+    tile_sig_set(c, p);
+    if (c->ev_after_fused) {   // iris_step: the metric leg starts behind the feature kernel
+        CU(cudaEventRecord(c->ev_after_fused, st));
+        c->ev_after_fused = nullptr;
+    }
     return IRIS_OK;
 }
 
@@ -214,6 +257,7 @@ int run_logmel_minmax(iris_ctx* c, FusedParams& p, float* d_out, cudaStream_t st
     }
     int rc = prepare_fused(c, p, FM_MEL, c->max_segs);
     if (rc) return rc;
+    tile_sig_set(c, p);   // (this path always runs k_tiles)
     const int per_clip_tiles = ((c->T + p.fr - 1) / p.fr) * p.n_pairs;
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (c->profile) {   // the roofline hook times k_tiles + k_fused of the first part
@@ -244,6 +288,35 @@ int run_logmel_minmax(iris_ctx* c, FusedParams& p, float* d_out, cudaStream_t st
     CU(cudaEventRecord(c->ev_join, c->aux));
     CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return IRIS_OK;
+}
+
+// FusedParams of a feature launch from waveform banks: everything but the output pointer and the
+// min-max scratch, including the tile-block scratch and its layout (prepare_fused)
+int feature_params(iris_ctx* c, int mode, int select, FusedParams& p) {
+    const bool mel = mode >= IRIS_FEAT_MEL;
+    fill_common(c, p);
+    p.segs = c->d_segs;
+    p.seg_ptr = c->d_seg_ptr;
+    p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
+    p.B = c->B; p.T = c->T;
+    set_geometry(c, p, c->C, mel);
+    p.c_out = c->c_out;
+    p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
+    p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
+    p.filter_k = c->filter_k;
+    p.remap = c->remap;
+    p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
+    if (select) {   // only_voice / only_noise: the plain mix of a subset, no masks / remap / filter
+        p.seg_select = select;
+        p.tmask = nullptr; p.fmask = nullptr; p.n_tmask = 0; p.n_fmask = 0;
+        p.filter_k = 0; p.remap = IRIS_REMAP_NONE; p.c_out = c->C;
+        set_geometry(c, p, c->C, false);
+    }
+    if (mel) {
+        p.do_log = mode != IRIS_FEAT_MEL;
+        p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
+    }
+    return prepare_fused(c, p, mel ? FM_MEL : mode, c->max_segs);
 }
 
 // Features from spectrogram banks: the mix + per-cell epilogue is one streaming kernel
@@ -644,6 +717,7 @@ int iris_bank_register(iris_ctx* c, int kind, int n_items, int n_chan, const flo
         set_geometry(c, p, n_chan, false);
         p.activity = b.activity.as<uint8_t>();
         rc = run_fused(c, p, FM_ACTIVITY, 1, st);
+        c->tile_sig.valid = false;   // the segment list of this pass is freed below
         if (rc) return rc;
         b.h_activity.resize(act_bytes);
         CU(cudaMemcpyAsync(b.h_activity.data(), b.activity.p, act_bytes, cudaMemcpyDeviceToHost, st));
@@ -983,6 +1057,7 @@ int iris_plan_upload(iris_ctx* c, const iris_plan* pl, iris_stream stream) {
     c->spec_mode = bg.spec;
     c->has_plan = true;
     c->labels_done = false;
+    c->tile_sig.valid = false;
     return IRIS_OK;
 }
 
@@ -991,7 +1066,7 @@ int iris_labels(iris_ctx* c, float* d_vtk, float* d_frame, uint8_t* d_keep, iris
     if (!c->has_plan) return fail(IRIS_ERR_STATE, "no plan uploaded");
     int rc = set_device(c);
     if (rc) return rc;
-    return run_labels(c, d_vtk, d_frame, d_keep, static_cast<cudaStream_t>(stream));
+    return run_labels(c, d_vtk, d_frame, d_keep, static_cast<cudaStream_t>(stream), c->feat_hint);
 }
 
 int iris_features(iris_ctx* c, int mode, float* d_out, iris_stream stream) {
@@ -1012,7 +1087,7 @@ int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_s
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!c->labels_done) {   // accept flags of the voices are an input of the mix
-        rc = run_labels(c, nullptr, nullptr, nullptr, st);
+        rc = run_labels(c, nullptr, nullptr, nullptr, st, select == IRIS_SELECT_ALL ? mode : -1);
         if (rc) return rc;
     }
     const bool mel = mode >= IRIS_FEAT_MEL;
@@ -1025,28 +1100,11 @@ int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_s
     if (mel && c->remap != IRIS_REMAP_NONE)
         return fail(IRIS_ERR_UNSUPPORTED, "mel features with a channel remap run unfused");
     FusedParams p;
-    fill_common(c, p);
-    p.segs = c->d_segs;
-    p.seg_ptr = c->d_seg_ptr;
-    p.keep = c->V > 0 ? c->keep.as<uint8_t>() : nullptr;
-    p.B = c->B; p.T = c->T;
-    set_geometry(c, p, c->C, mel);
-    p.c_out = c->c_out;
-    p.tmask = c->d_tmask; p.n_tmask = c->n_tmask;
-    p.fmask = c->d_fmask; p.n_fmask = c->n_fmask;
-    p.filter_k = c->filter_k;
-    p.remap = c->remap;
-    p.merge_f = c->d_merge_f; p.merge_sf = c->d_merge_sf;
+    rc = feature_params(c, mode, select, p);
+    if (rc) return rc;
     p.out = d_out;
-    if (select) {   // only_voice / only_noise: the plain mix of a subset, no masks / remap / filter
-        p.seg_select = select;
-        p.tmask = nullptr; p.fmask = nullptr; p.n_tmask = 0; p.n_fmask = 0;
-        p.filter_k = 0; p.remap = IRIS_REMAP_NONE; p.c_out = c->C;
-        set_geometry(c, p, c->C, false);
-    }
+    c->feat_hint = select == IRIS_SELECT_ALL ? mode : -1;
     if (mel) {
-        p.do_log = mode != IRIS_FEAT_MEL;
-        p.do_minmax = mode == IRIS_FEAT_LOGMEL_MINMAX;
         if (p.do_minmax) {   // per-clip (~min, max) bit patterns; k_logmel_post leaves them
                              // zeroed, so only a fresh allocation is cleared
             const void* before = c->minmax.p;
@@ -1095,7 +1153,9 @@ int iris_stft(iris_ctx* c, const float* wav, int n_chan, int64_t n, int normaliz
     p.B = 1; p.T = int32_t(kT);
     set_geometry(c, p, n_chan, false);
     p.out = d_out;
-    return run_fused(c, p, FM_COMPLEX, 1, st);
+    rc = run_fused(c, p, FM_COMPLEX, 1, st);
+    c->tile_sig.valid = false;   // the one-segment list of this call is rewritten by the next one
+    return rc;
 }
 
 int iris_metric_counts(iris_ctx* c, const float* y_true, const float* y_pred, int B, int T, int K,

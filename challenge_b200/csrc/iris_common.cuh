@@ -58,6 +58,8 @@ struct FusedParams {
     int32_t tile_stride;
     int32_t max_segs;            // most mixing segments any clip has
     int32_t chunk;               // consecutive tiles per work claim
+    int32_t n_big, n_mid;        // claim schedule (launch_fused): n_big claims of `chunk` tiles, n_mid of
+    int32_t chunk_mid, chunk_tail;   // `chunk_mid`, the rest `chunk_tail`
     int32_t tile_first, tile_count;   // tiles [tile_first, tile_first + tile_count) of the batch belong to this launch
     int32_t seg_select;          // 0: every segment; 1: voices only; 2: background + noises only
                                  // (only_voice / only_noise of pipeline.py:37-38, 82-83, 104-108)
@@ -85,6 +87,10 @@ struct FusedParams {
     const float4* tw1;      // [8][32] {W512^(n2*2q), W512^(n2*(2q+1))}
     const float4* ts;       // [8][2]  {t(2m), t(2m+1)}, t(i) = par ? W32^i : 1
     const float* hann;      // [512] periodic Hann
+#ifdef IRIS_TRACE
+    unsigned long long* trace;   // experiment builds (scripts/trace_fused.py): [grid + 1][64] time stamps
+    int32_t trace_grid;
+#endif
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA 1-D) ----

@@ -89,6 +89,16 @@ struct iris_ctx {
     DevBuf keep, minmax, scratch_labels, stft_pad, stft_small;   // minmax: [B,2] + done [B]
     DevBuf tiles, sched;
     int max_segs = 1;
+    // tile blocks built by k_labels for the feature launch that follows (iris_abi.cu: run_labels):
+    // the layout they were built for; a feature launch with another one runs k_tiles
+    struct TileSig {
+        bool valid = false;
+        const void *segs = nullptr, *keep = nullptr;   // the plan (a plan upload invalidates as well)
+        int B = 0, T = 0;
+        int fm_bits = 0, seg_select = 0, fr = 0, n_pairs = 0, max_segs = 0, stride = 0, masks = 0, filter_k = 0;
+    } tile_sig;
+    int feat_hint = -1;   // feature mode of the last feature launch: what k_labels builds tile blocks for
+    cudaEvent_t ev_after_fused = nullptr;   // recorded (once) right behind the next k_fused launch (iris_step)
     // pinned staging for the plan blob: a ring, so that the host can run up to kStageRing batches
     // ahead of the device before it has to wait for an upload to drain
     static constexpr int kStageRing = 4;

@@ -7,7 +7,9 @@ namespace iris {
 
 struct FusedParams;
 
-enum { FUSED_LAUNCH_TILES = 1, FUSED_LAUNCH_KERNEL = 2 };
+// FUSED_LAUNCH_PDL: launch k_fused with programmatic stream serialization although k_tiles is not
+// launched in front of it (the kernel in front -- k_labels -- triggers early and wrote the tile blocks)
+enum { FUSED_LAUNCH_TILES = 1, FUSED_LAUNCH_KERNEL = 2, FUSED_LAUNCH_PDL = 4 };
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream,
                          int what = FUSED_LAUNCH_TILES | FUSED_LAUNCH_KERNEL);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
@@ -44,7 +46,9 @@ struct LabelParams {
     float* frame_labels;         // [B,T,K]
     uint8_t* keep;               // [B,V]
 };
-cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream);
+// tiles != null: every CTA also builds the tile blocks of its clip for the k_fused launch that
+// follows (tiles->keep must be p.keep, tiles->tile_blocks sized by fused_tile_bytes)
+cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream, const FusedParams* tiles = nullptr);
 
 // k_metrics.cu
 cudaError_t launch_metric_counts(const float* y_true, const float* y_pred, int B, int T, int Tp, int K,

@@ -381,11 +381,27 @@ int iris_step(iris_ctx* c, const iris_step_config* cfg, const iris_step_io* io, 
         for (auto& l : c->legs)
             if (l.seq && l.labels == io->d_frame_labels) CU(cudaStreamWaitEvent(st, l.done, 0));
     if (V > 0) {
+        c->feat_hint = cfg->feature_mode;   // k_labels also builds the tile blocks of the feature launch
         rc = iris_labels(c, io->d_labels_vtk, io->d_frame_labels, io->d_keep, stream);
         if (rc) return rc;
     }
+    // The metric leg needs the labels only.  For the min-max log-mel features it is forked BEHIND
+    // k_fused and runs beside k_logmel_post (31 us, the leg takes ~10): k_labels -> k_fused stay
+    // adjacent in the stream, so k_fused's programmatic launch overlaps its prologue with k_labels.
+    // Other modes have no second pass to hide the leg behind: it forks right behind k_labels.
+    static const bool late_env = getenv("IRIS_METRIC_LATE") ? atoi(getenv("IRIS_METRIC_LATE")) != 0 : true;
+    const bool late = metric && late_env && cfg->feature_mode == IRIS_FEAT_LOGMEL_MINMAX && !c->spec_mode;
+    if (late) {
+        c->ev_after_fused = c->ev_labels;
+        rc = iris_features(c, cfg->feature_mode, io->d_features, stream);
+        if (rc) return rc;
+        if (c->ev_after_fused) {   // the feature path did not go through run_fused
+            c->ev_after_fused = nullptr;
+            CU(cudaEventRecord(c->ev_labels, st));
+        }
+    }
     if (metric) {
-        CU(cudaEventRecord(c->ev_labels, st));
+        if (!late) CU(cudaEventRecord(c->ev_labels, st));
         CU(cudaStreamWaitEvent(c->side, c->ev_labels, 0));
         const int K = vb.n_classes;
         CU(launch_metric_counts(io->d_frame_labels, io->d_y_pred, B, c->T, c->T, K,
@@ -406,6 +422,7 @@ int iris_step(iris_ctx* c, const iris_step_config* cfg, const iris_step_io* io, 
         leg.labels = io->d_frame_labels;
         leg.seq = c->step_seq;
     }
+    if (late) return IRIS_OK;
     return iris_features(c, cfg->feature_mode, io->d_features, stream);
 }
 

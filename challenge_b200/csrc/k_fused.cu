@@ -36,11 +36,30 @@
 #include "iris_common.cuh"
 #include "iris_epilogue.cuh"
 #include "iris_launch.h"
+#include "iris_tiles.cuh"
 
 namespace iris {
 
+// Experiment builds (-DIRIS_TRACE, scripts/trace_fused.py): per-CTA time stamps of the ramp-up, the
+// steady state and the tail of the persistent kernel.  Slot 0 / 10 are %globaltimer (aligns the
+// CTAs), the others clock64 of the SM.  Compiled out of the product build.
+#ifdef IRIS_TRACE
+__device__ __forceinline__ unsigned long long tr_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define IRIS_TR(slot, val)                                                                   \
+    do {                                                                                     \
+        if (p.trace) p.trace[size_t(blockIdx.x) * 64 + (slot)] = (unsigned long long)(val);  \
+    } while (0)
+#define IRIS_TRC(slot) IRIS_TR(slot, clock64())
+#else
+#define IRIS_TR(slot, val) do { } while (0)
+#define IRIS_TRC(slot) do { } while (0)
+#endif
+
 constexpr int kRing = 8;         // TileBlock ring entries (> stage buffers + 1, see the producer)
-constexpr int kMaxStages = 24;   // mixing segments of one clip (upper bound on stages per tile; the ring copy takes <= 30)
 #ifndef IRIS_MAX_FR
 #define IRIS_MAX_FR 16
 #endif
@@ -51,24 +70,6 @@ constexpr int kMaxFR = IRIS_MAX_FR;   // consumer warps per CTA (sets the regist
 constexpr int kMaxMel = 128;
 constexpr int kMaxTaps = 64;     // sum over the 32-filter rounds of the longest filter
 constexpr int kMaxFilter = 16;   // taps of the longest mel filter the fused epilogue takes
-
-struct StageDesc {
-    const float* src;      // first row of the stage in the pair plane of the source
-    uint16_t j_lo, j_cnt;  // tile-relative frames [j_lo, j_lo + j_cnt); j_cnt == 0: empty stage
-    float gain;            // 0.5 * gain (the 1/2 of the two-channel split)
-};
-static_assert(sizeof(StageDesc) == 16, "StageDesc layout");
-
-struct TileBlock {
-    int32_t n;             // stages (>= 1)
-    int32_t b;             // clip
-    int32_t t0_pair;       // first frame | pair << 24
-    uint32_t tmask_bits;   // bit j: frame t0 + j is time-masked (transforms.py:12-40)
-    int16_t fm[8];         // (size, offset) x 4 frequency masks of the clip
-    StageDesc d[kMaxStages];
-};
-static_assert(sizeof(TileBlock) == 32 + 16 * kMaxStages, "TileBlock layout");
-constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
 // ---- shared memory map (bytes) ----
 constexpr int OFF_FULL = 0;                                  // uint64 full[<= 3]
@@ -104,89 +105,23 @@ __host__ __device__ inline bool stages_output(int mode, int remap, int fr) {
     return mode != FM_MEL && mode != FM_ACTIVITY && remap == REMAP_NONE && fr == 8;
 }
 
-// ---- pre-kernel: one thread per tile builds its TileBlock ----
+// ---- pre-kernel: one thread per tile builds its TileBlock (launches without a k_labels pass in
+// front, or whose tile layout differs from the one k_labels was asked to build) ----
 __global__ void __launch_bounds__(128) k_tiles(const FusedParams p) {
-    const int FR = p.fr;
-    const int tpc = (p.T + FR - 1) / FR;
-    const int per_clip = tpc * p.n_pairs;
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    // programmatic dependent launch: k_fused may start its prologue (tables, barriers, zero fill of
-    // the stage buffers) now; it waits for this grid before it touches a tile block
+    // programmatic dependent launch: k_fused may start its prologue (barriers, zero fill of the stage
+    // buffers) now; it waits for this grid before it touches a tile block
     cudaTriggerProgrammaticLaunchCompletion();
+#ifdef IRIS_TRACE
+    if (p.trace && tile == 0) p.trace[size_t(p.trace_grid) * 64] = tr_gtimer();
+#endif
+    const int per_clip = ((p.T + p.fr - 1) / p.fr) * p.n_pairs;
     if (tile >= p.B * per_clip) return;
     if (tile < p.B && p.minmax != nullptr) {   // per-clip extrema scratch of the launch that follows
         p.minmax[2 * tile] = 0u;
         p.minmax[2 * tile + 1] = 0u;
     }
-    // tile order: clip, then time, then channel pair -- the pairs of one (clip, time) range are
-    // consecutive tiles (same work chunk), so the partial sectors they write to the same
-    // out[b, f, t, :] rows merge in L2 within microseconds
-    const int b = tile / per_clip;
-    const int r = tile - b * per_clip;
-    const int pair = r % p.n_pairs;
-    const int t0 = (r / p.n_pairs) * FR;
-    const int t_end = min(t0 + FR, p.T);
-    unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
-    StageDesc* d = reinterpret_cast<StageDesc*>(blk + 32);
-    int n = 0;
-    const int s1 = p.seg_ptr[b + 1];
-    for (int s = p.seg_ptr[b]; s < s1; ++s) {
-        const Seg sg = p.segs[s];
-        const int lo = max(sg.t_lo, t0), hi = min(sg.t_hi, t_end);
-        if (lo >= hi || (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0)) continue;
-        if ((p.seg_select == 1 && sg.keep_idx < 0) || (p.seg_select == 2 && sg.keep_idx >= 0)) continue;
-        if (n < p.max_segs) {
-            StageDesc e;
-            e.src = sg.base + size_t(pair) * size_t(sg.pair_stride) + size_t(lo + sg.shift) * 512;
-            e.j_lo = uint16_t(lo - t0);
-            e.j_cnt = uint16_t(hi - lo);
-            e.gain = 0.5f * sg.gain;   // exact; folds the 1/2 of the two-channel split
-            d[n++] = e;
-        }
-    }
-    if (n == 0) {   // nothing overlaps: one empty stage keeps the slot protocol uniform
-        StageDesc e;
-        e.src = nullptr; e.j_lo = 0; e.j_cnt = 0; e.gain = 0.f;
-        d[n++] = e;
-    }
-    uint32_t tbits = 0;
-    if (p.tmask != nullptr) {
-        const int32_t* tm = p.tmask + size_t(b) * p.n_tmask * 2;
-        for (int i = 0; i < p.n_tmask; ++i) {
-            const int size = tm[2 * i], off = tm[2 * i + 1];
-            const int lo = max(off, t0), hi = min(off + size, t_end);
-            if (lo < hi) tbits |= ((1u << (hi - lo)) - 1u) << (lo - t0);
-        }
-    }
-    int4 hdr;
-    hdr.x = n; hdr.y = b; hdr.z = t0 | (pair << 24); hdr.w = int(tbits);
-    *reinterpret_cast<int4*>(blk) = hdr;
-    if (p.fm_bits) {
-        // mel epilogues that need bins below 128 only: the bins zeroed by the frequency masks and
-        // stft_filter as a 128-bit map, so that a lane picks up its four bits with four shifts
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        auto zero_bins = [&](int off, int size) {
-            for (int f = max(off, 0); f < min(off + size, 128); ++f) w[f >> 5] |= 1u << (f & 31);
-        };
-        if (p.fmask != nullptr) {
-            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
-            for (int i = 0; i < p.n_fmask; ++i) zero_bins(fk[2 * i + 1], fk[2 * i]);
-        }
-        if (p.filter_k > 0) zero_bins(1, p.filter_k);
-        *reinterpret_cast<uint4*>(blk + 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        int16_t fm[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) fm[i] = 0;
-        if (p.fmask != nullptr) {
-            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
-            for (int i = 0; i < p.n_fmask && i < 4; ++i) {
-                fm[2 * i] = int16_t(fk[2 * i]);
-                fm[2 * i + 1] = int16_t(fk[2 * i + 1]);
-            }
-        }
-        *reinterpret_cast<int4*>(blk + 16) = *reinterpret_cast<const int4*>(fm);
-    }
+    build_tile_block(p, tile, per_clip);
 }
 
 // one (bin, frame, channel pair) of the spectrogram modes without a channel remap:
@@ -273,6 +208,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const int warp = tid >> 5, lane = tid & 31;
     // fixed variants: 8 frames per tile and the 12 taps of the default mel shape, so that the
     // shared-memory map folds into immediates
+    if (tid == 0) { IRIS_TR(0, tr_gtimer()); IRIS_TRC(1); }
     const int FR = kFix ? IRIS_FIX_FR : p.fr;
     const int mel_taps = kFix ? (fixed_mel_L(0) + fixed_mel_L(1) + fixed_mel_L(2)) : p.mel_taps;
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_FULL);
@@ -281,21 +217,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const uint32_t slotB = slot_bytes(FR);
     unsigned char* slots = sm + off_slots(mel_taps, FR);
 
-    // ---- one-time setup: tables, barriers, finite data in the stage buffers ----
+    // ---- one-time setup: barriers, finite data in the stage buffers (the tables are loaded by the
+    // consumer warps while the producer warp is already fetching the first tile) ----
     {
-        // base powers of the inter-pass twiddle (fftwarp.cuh): p.tw1[q][n2] = {w^(2q), w^(2q+1)}
-        float4* s_tw1 = reinterpret_cast<float4*>(sm + OFF_TW1);
-        if (tid < 32) {
-            const float4 q0 = p.tw1[tid], q1 = p.tw1[32 + tid], q2 = p.tw1[64 + tid], q4 = p.tw1[128 + tid];
-            s_tw1[tid] = make_float4(q0.z, q0.w, q1.x, q1.y);
-            s_tw1[32 + tid] = make_float4(q2.x, q2.y, q4.x, q4.y);
-        }
-        if (kMel) {
-            uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
-            for (int i = tid; i < kMaxMel; i += blockDim.x) s_ms[i] = p.mel_info[i];   // [4 rounds][32 lanes]
-            float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
-            for (int i = tid; i < mel_taps * 32; i += blockDim.x) s_mw[i] = p.mel_w[i];
-        }
         // rows of a slot outside a stage's frame range are read (and multiplied by 0) by the
         // frames the stage does not cover: they must hold finite numbers
         float4* z = reinterpret_cast<float4*>(slots);
@@ -310,42 +234,62 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         fence_proxy_async();   // the zero fill (generic proxy) precedes the bulk copies (async proxy)
         __syncthreads();
     }
+    if (tid == 0) IRIS_TRC(2);
     // everything above overlapped k_tiles (programmatic dependent launch); its tile blocks and the
     // zeroed extrema scratch are visible from here on
     cudaGridDependencySynchronize();
+    if (tid == 0) IRIS_TRC(3);
 
     if (warp == FR) {
         // =========================== producer warp ===========================
         // The producer is at most S stages ahead of the slowest consumer and every tile
         // has at least one stage, so when it writes ring entry i the slowest consumer is
         // still in tile >= i - S - 1: kRing > S + 1 entries never collide.
-        // Work is claimed in chunks of p.chunk consecutive tiles from a global counter (the
-        // next claim is issued one chunk ahead, so its latency is hidden): consecutive tiles of
-        // a clip mostly stay on one SM (per-clip state changes rarely, the row shared by two
-        // tiles is re-read one tile later) and the SMs still finish together.
         uint32_t slot = 0, phase = 0;
         const uint64_t pol_stream = l2_policy_evict_first();
         const int chunks16 = p.tile_stride >> 4;
-        const int CH = p.chunk;
+        // Work claims (launch_fused sets the schedule): claim q covers p.chunk consecutive tiles for
+        // q < n_big, then p.chunk_mid tiles for n_mid claims, then p.chunk_tail tiles -- the chunks
+        // shrink towards the end of the launch so that the CTAs finish within about one tile of each
+        // other (whole chunks to the end left the slower CTA of an SM up to two chunks, ~20 us, behind).
+        // The first claim of a CTA is its block index, the later ones come from a global counter and
+        // are issued when the LAST tile of the current claim starts: a CTA never owns more than one
+        // chunk.  Consecutive tiles of a clip mostly stay on one SM (per-clip state changes rarely,
+        // the row shared by two tiles is re-read one tile later).
+        const int CH = p.chunk, CM = p.chunk_mid, CT = p.chunk_tail;
+        const long long n_big = p.n_big, n_mid = p.n_mid;
+        auto claim_range = [&](long long q, int& len) -> long long {
+            if (q < n_big) { len = CH; return q * CH; }
+            q -= n_big;
+            if (q < n_mid) { len = CM; return n_big * CH + q * CM; }
+            len = CT;
+            return n_big * CH + n_mid * CM + (q - n_mid) * CT;
+        };
+        auto load_block = [&](int tile) -> int4 {
+            const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
+            return lane < chunks16 ? __ldg(reinterpret_cast<const int4*>(blk) + lane) : make_int4(0, 0, 0, 0);
+        };
         int i = 0;
-        unsigned next = 0;
-        if (lane == 0) next = atomicAdd(&p.sched[0], 1u);
-        while (true) {
-            const long long first = (long long)__shfl_sync(0xffffffffu, next, 0) * CH;
-            if (first >= n_tiles) break;
-            if (lane == 0) next = atomicAdd(&p.sched[0], 1u);
-            const int last = int(min((long long)n_tiles, first + CH));
-            for (int tile = int(first); tile < last; ++tile, ++i) {
-                const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
+        int len = 0;
+        long long first = claim_range(blockIdx.x, len);
+        if (lane == 0) IRIS_TRC(4);
+        if (first < n_tiles) {
+            int tile = int(first);
+            int last = int(min((long long)n_tiles, first + len));
+            int4 c = load_block(tile);
+            while (true) {
                 unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
-                int4 c = make_int4(0, 0, 0, 0);
-                if (lane < chunks16) {
-                    c = __ldg(reinterpret_cast<const int4*>(blk) + lane);
-                    *reinterpret_cast<int4*>(ent + 16 * lane) = c;
-                }
+                if (lane < chunks16) *reinterpret_cast<int4*>(ent + 16 * lane) = c;
                 __syncwarp();
                 const int n = __shfl_sync(0xffffffffu, c.x, 0);
                 const TileBlock* tb = reinterpret_cast<const TileBlock*>(ent);
+                // look ahead: the block of the next tile of this claim is fetched while the stages of
+                // this one are issued; at the last tile of a claim the next claim goes out instead
+                const bool more = tile + 1 < last;
+                unsigned nxt = 0;
+                int4 c2 = make_int4(0, 0, 0, 0);
+                if (more) c2 = load_block(tile + 1);
+                else if (lane == 0) nxt = atomicAdd(&p.sched[0], 1u);
                 for (int s = 0; s < n; ++s) {
                     // the whole warp waits (one instruction per poll either way) so that it stays
                     // converged
@@ -361,15 +305,29 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                                 bulk_g2s_hint(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot], pol_stream);
                             else
                                 bulk_g2s(slots + slot * slotB + uint32_t(d.j_lo) * 2048u, d.src, bytes, &full[slot]);
+                            if (i == 0 && s == 0) IRIS_TRC(5);
                         }
                     }
                     if (++slot == S) { slot = 0; phase ^= 1u; }
+                }
+                ++i;
+                if (more) {
+                    ++tile;
+                    c = c2;
+                } else {
+                    const long long q = (long long)__shfl_sync(0xffffffffu, nxt, 0) + gridDim.x;
+                    first = claim_range(q, len);
+                    if (first >= n_tiles) break;
+                    tile = int(first);
+                    last = int(min((long long)n_tiles, first + len));
+                    c = load_block(tile);
                 }
             }
         }
         // no work left to claim: a kernel launched behind this one with programmatic stream
         // serialization (k_logmel_post) may be scheduled; it still waits for the whole grid
         cudaTriggerProgrammaticLaunchCompletion();
+        if (lane == 0) { IRIS_TRC(11); IRIS_TR(9, i); }
         // end marker: a TileBlock with n == 0 behind one more (empty) stage
         {
             unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
@@ -387,6 +345,22 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         }
     } else {
         // =========================== consumer warps ===========================
+        {
+            // base powers of the inter-pass twiddle (fftwarp.cuh): p.tw1[q][n2] = {w^(2q), w^(2q+1)}
+            float4* s_tw1 = reinterpret_cast<float4*>(sm + OFF_TW1);
+            if (tid < 32) {
+                const float4 q0 = p.tw1[tid], q1 = p.tw1[32 + tid], q2 = p.tw1[64 + tid], q4 = p.tw1[128 + tid];
+                s_tw1[tid] = make_float4(q0.z, q0.w, q1.x, q1.y);
+                s_tw1[32 + tid] = make_float4(q2.x, q2.y, q4.x, q4.y);
+            }
+            if (kMel) {
+                uint32_t* s_ms = reinterpret_cast<uint32_t*>(sm + OFF_MSTART);
+                for (int i = tid; i < kMaxMel; i += FR * 32) s_ms[i] = p.mel_info[i];   // [4 rounds][32 lanes]
+                float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
+                for (int i = tid; i < mel_taps * 32; i += FR * 32) s_mw[i] = p.mel_w[i];
+            }
+            named_bar_sync(2, FR * 32);   // consumer warps only
+        }
         const int j = warp;                        // tile-relative frame of this warp
         const int k1 = warp_k1(lane), par = warp_par(lane);
         const float sgn = par ? -1.f : 1.f;
@@ -407,7 +381,11 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
+#ifdef IRIS_EXP_NORED
+            const bool go = false;
+#else
             const bool go = lane == 0 && mn <= mx;
+#endif
             red_max_u32_if(&p.minmax[2 * mm_clip], ~__float_as_uint(mn), go);
             red_max_u32_if(&p.minmax[2 * mm_clip + 1], __float_as_uint(mx), go);
             mn = __int_as_float(0x7f800000);
@@ -417,7 +395,11 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         uint32_t slot = 0, phase = 0;
         const uint64_t pol_keep = l2_policy_evict_last();
         // mel rows are re-read by k_logmel_post: keep them in L2 (fixed variants: hints are on)
+#ifdef IRIS_EXP_NOHINT
+        const bool keep_l2 = false;
+#else
         const bool keep_l2 = kFix ? bool(EPI & EPI_MINMAX) : (kMel && p.l2_hints && do_minmax);
+#endif
         float* clip_out = p.out;      // out[b, 0, 0, 0] of the current clip (mel modes)
         uint32_t zbits = 0;
         int zb_clip = -1;
@@ -429,6 +411,12 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             mbar_wait_parked(&full[slot], phase);           // also publishes the TileBlock of this tile
             const int4 hdr = *reinterpret_cast<const int4*>(tb);
             const int n_st = hdr.x;
+            if (i == 0 && tid == 0) IRIS_TRC(6);
+#ifdef IRIS_TRACE
+            if (tid == 0 && i > 0 && (i & 1) == 0 && (i >> 1) < 48) IRIS_TRC(16 + (i >> 1));   // tiles 0 .. i-1 done
+            if (tid == 0 && i == 1) IRIS_TRC(7);
+            if (tid == 0 && i == 21) IRIS_TRC(12);
+#endif
             if (n_st == 0) break;                    // end marker
             // (skipping the row reads of time-masked frames -- ~11 % of the frames -- was measured on
             // B200: +2..5 % kernel time; the extra branch costs registers (93 -> 96 + a spill) and the
@@ -465,6 +453,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 if (++slot == S) { slot = 0; phase ^= 1u; }
             }
 
+            if (tid == 0 && i == 21) IRIS_TRC(13);   // mix of tile 21 done
             const int b = hdr.y;
             const int pair = kFix ? 0 : (hdr.z >> 24);
             const int t = (hdr.z & 0xffffff) + j;
@@ -536,6 +525,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 __syncwarp();   // every lane is done with the exchange rows (reused for |X| below)
             }
 
+            if (tid == 0 && i == 21) IRIS_TRC(14);   // FFT of tile 21 done
             // ---- epilogue ----
             // register jj holds bin f = k1 + 16 (2 jj + par); its mirror 512 - f is register
             // 15 - jj of the partner lane (lane 0: its own register (16 - jj) & 15)
@@ -611,7 +601,11 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         if (mrow != 0xffffu) {
                             float* o = o_t + mrow * row_elems;
                             float a0 = acc0[r], a1 = acc1[r];
+#ifdef IRIS_EXP_NOMM
+                            if (false) {
+#else
                             if (do_minmax) {
+#endif
                                 mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
                                 mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
                             }
@@ -721,6 +715,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             }
         }
         if (kMel && do_minmax && mm_clip >= 0) flush_minmax();
+        if (tid == 0) { IRIS_TRC(8); IRIS_TR(10, tr_gtimer()); }
     }
 }
 
@@ -758,6 +753,76 @@ size_t fused_tile_bytes(const FusedParams& p, int* stride_out) {
 // p.tile_blocks (fused_tile_bytes) is provided by the caller.  what: FUSED_LAUNCH_TILES builds the tile
 // blocks of the whole batch (k_tiles), FUSED_LAUNCH_KERNEL runs k_fused on the tiles
 // [p.tile_first, p.tile_first + p.tile_count) (tile_count 0: all of them).
+// Claim schedule of a launch (see the producer warp): whole chunks first, then half chunks for the
+// last kTailMid tiles per CTA, single tiles (tile pairs of a 4-channel clip) for the last kTailOne.
+// Measured on B200 (profiles/r02_trace_*.txt): with whole chunks to the end the CTAs of a 256-clip
+// launch finish 22 us apart (the slower of the two CTAs of an SM needs ~13 us for a chunk of 4 and
+// used to own a second one).
+static void fused_schedule(FusedParams& p, long long n_tiles, int grid) {
+    static int t_one = -1, t_mid = -1;
+    if (t_one < 0) {
+        const char* e1 = getenv("IRIS_TAIL1");
+        const char* e2 = getenv("IRIS_TAIL2");
+        t_one = e1 ? atoi(e1) : 2;
+        t_mid = e2 ? atoi(e2) : 4;
+    }
+    const int unit = p.pair_merge ? 2 : 1;   // both channel pairs of a (clip, time) range in one claim
+    p.chunk_tail = unit;
+    p.chunk_mid = p.chunk / 2 > unit ? p.chunk / 2 : unit;
+    if (p.chunk <= unit) {   // nothing to shrink
+        p.chunk_mid = p.chunk_tail = p.chunk;
+        p.n_big = 0x7fffffff;
+        p.n_mid = 0;
+        return;
+    }
+    const long long tail_one = (long long)grid * t_one, tail_mid = (long long)grid * t_mid;
+    const long long rem = n_tiles > tail_one ? n_tiles - tail_one : 0;
+    const long long mid = rem < tail_mid ? rem : tail_mid;
+    p.n_big = int32_t((rem - mid) / p.chunk);
+    p.n_mid = int32_t((rem - (long long)p.n_big * p.chunk) / p.chunk_mid);
+}
+
+#ifdef IRIS_TRACE
+// the stamps of the last launch go to $IRIS_TRACE_FILE as raw uint64 [grid + 1][64]
+static unsigned long long* g_trace_buf = nullptr;
+static size_t g_trace_cap = 0;
+static int g_trace_grid = 0;
+static void trace_begin(FusedParams& p, int num_sms, cudaStream_t stream) {
+    p.trace = nullptr;
+    p.trace_grid = 0;
+    if (!getenv("IRIS_TRACE_FILE")) return;
+    const size_t need = size_t(num_sms * 4 + 1) * 64 * 8;
+    if (g_trace_cap < need) {
+        cudaFree(g_trace_buf);
+        cudaMalloc(&g_trace_buf, need);
+        g_trace_cap = need;
+    }
+    cudaMemsetAsync(g_trace_buf, 0, need, stream);
+    p.trace = g_trace_buf;
+    p.trace_grid = num_sms * 4;   // row of the k_tiles stamp
+    g_trace_grid = num_sms * 4;
+}
+static void trace_end(int grid, cudaStream_t stream) {
+    const char* f = getenv("IRIS_TRACE_FILE");
+    if (!f || !g_trace_buf) return;
+    cudaStreamSynchronize(stream);
+    (void)grid;
+    const size_t n = size_t(g_trace_grid + 1) * 64;
+    unsigned long long* h = static_cast<unsigned long long*>(malloc(n * 8));
+    cudaMemcpy(h, g_trace_buf, n * 8, cudaMemcpyDeviceToHost);
+    if (FILE* fp = fopen(f, "wb")) {
+        fwrite(h, 8, n, fp);
+        fclose(fp);
+    }
+    free(h);
+}
+#define IRIS_TRACE_BEGIN(grid)
+#define IRIS_TRACE_END(grid) trace_end(grid, stream);
+#else
+#define IRIS_TRACE_BEGIN(grid)
+#define IRIS_TRACE_END(grid)
+#endif
+
 cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStream_t stream, int what) {
     FusedParams p = p_in;
     const int FR = p.fr;
@@ -772,12 +837,15 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
     if (mode == FM_MEL && (long long)p.n_mel * p.T * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;   // 32-bit row offsets inside a clip
     const size_t smem = fused_smem_bytes(p, mode);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
+#ifdef IRIS_TRACE
+    trace_begin(p, num_sms, stream);
+#endif
     if (what & FUSED_LAUNCH_TILES) k_tiles<<<unsigned((all_tiles + 127) / 128), 128, 0, stream>>>(p);
     if (!(what & FUSED_LAUNCH_KERNEL)) return cudaGetLastError();
     const int threads = (FR + 1) * 32;
     // programmatic dependent launch behind k_tiles of the same call (prologue overlap); a launch on
     // its own (later part of a split batch) is an ordinary one
-    const int pdl = (what & FUSED_LAUNCH_TILES) && !getenv("IRIS_NO_PDL") ? 1 : 0;
+    const int pdl = (what & (FUSED_LAUNCH_TILES | FUSED_LAUNCH_PDL)) && !getenv("IRIS_NO_PDL") ? 1 : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     // persistent grid: as many CTAs as are resident at once, asked of the occupancy calculator once
@@ -812,6 +880,7 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
         }                                                                                       \
         const long long max_ctas = (long long)num_sms * per_sm;                                 \
         const int grid = int(n_tiles < max_ctas ? n_tiles : max_ctas);                          \
+        fused_schedule(p, n_tiles, grid);                                                       \
         cudaLaunchConfig_t cfg{};                                                               \
         cfg.gridDim = dim3(unsigned(grid));                                                     \
         cfg.blockDim = dim3(unsigned(threads));                                                 \
@@ -822,8 +891,10 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
         attr[0].val.programmaticStreamSerializationAllowed = pdl;                               \
         cfg.attrs = attr;                                                                       \
         cfg.numAttrs = 1;                                                                       \
+        IRIS_TRACE_BEGIN(grid)                                                                  \
         cudaError_t le = cudaLaunchKernelEx(&cfg, k_fused<M, NJV, EPIV>, p);                    \
         if (le != cudaSuccess) return le;                                                       \
+        IRIS_TRACE_END(grid)                                                                    \
     }
     switch (mode) {
         case FM_COMPLEX: IRIS_LAUNCH(FM_COMPLEX, 8, 0) break;

@@ -4,17 +4,26 @@
 // activity flags (activity = reduce_max(voice, (f, 2C)) > 0, pipeline.py:55).
 // One CTA per clip; voices are visited in order because acceptance of voice v depends
 // on the labels of the voices accepted before it (pipeline.py:78-84).
+#include <cstring>
+
 #include "iris_common.cuh"
 #include "iris_launch.h"
+#include "iris_tiles.cuh"
 
 namespace iris {
 
 // Shared memory: the running frame labels L[T*K] (float) and the activity bytes of the
 // clip's voices act[V][T], gathered up front so that the sequential per-voice passes run from
 // shared memory (one global round trip per clip instead of two per voice).
-__global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
+// build_tiles: the CTA also writes the tile blocks of its clip (iris_tiles.cuh) for the k_fused
+// launch behind it: the keep flags it has just decided are their only input that is not in the plan.
+__global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int build_tiles,
+                                                 const __grid_constant__ FusedParams fp) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int b = blockIdx.x;
+    // a feature kernel launched behind this one with programmatic stream serialization may start
+    // its prologue; it waits for the whole grid before it reads a tile block
+    cudaTriggerProgrammaticLaunchCompletion();
     const int TK = p.T * p.K;
     float* L = reinterpret_cast<float*>(s_raw);                       // [T*K]
     float* lab = L + TK;                                               // [V*K]
@@ -80,9 +89,13 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p) {
     __syncthreads();   // the final copy below walks L with another thread-to-element map
     float* out = p.frame_labels + size_t(b) * TK;
     for (int i = threadIdx.x; i < TK; i += blockDim.x) out[i] = L[i];
+    if (build_tiles) {   // (the barrier above also orders thread 0's keep flags before these reads)
+        const int per_clip = ((fp.T + fp.fr - 1) / fp.fr) * fp.n_pairs;
+        for (int r = threadIdx.x; r < per_clip; r += blockDim.x) build_tile_block(fp, b * per_clip + r, per_clip);
+    }
 }
 
-cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream) {
+cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream, const FusedParams* tiles) {
     if (p.B <= 0) return cudaSuccess;
     const size_t smem = (size_t(p.T) * p.K + size_t(p.V) * p.K) * 4 + size_t(p.V) * p.T;
     if (smem > 200 * 1024 || p.V > 64) return cudaErrorInvalidValue;
@@ -94,7 +107,10 @@ cudaError_t launch_labels(const LabelParams& p, cudaStream_t stream) {
     }
     // 1024 threads per clip: one frame per thread, so the sequential per-voice passes are a
     // handful of instructions per warp (256 threads measured 17 us, latency-bound)
-    k_labels<<<p.B, 1024, smem, stream>>>(p);
+    if (tiles && (tiles->keep != p.keep || tiles->B != p.B)) return cudaErrorInvalidValue;
+    FusedParams none;
+    if (!tiles) memset(&none, 0, sizeof none);
+    k_labels<<<p.B, 1024, smem, stream>>>(p, tiles ? 1 : 0, tiles ? *tiles : none);
     return cudaGetLastError();
 }
 
