@@ -190,6 +190,15 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// L2 prefetch of a span that a bulk copy will fetch shortly (no shared memory involved)
+__device__ __forceinline__ void bulk_prefetch_l2_if(const void* src_gmem, uint32_t bytes, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src_gmem),
+        "r"(bytes), "r"(uint32_t(pred))
+        : "memory");
+}
 __device__ __forceinline__ void st_f2_hint(float* addr, float a, float b, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(policy)
                  : "memory");

@@ -197,6 +197,9 @@ __host__ __device__ constexpr int fixed_mel_L(int r) { return r == 0 ? 2 : (r ==
 template <int MODE, int NJ, int EPI>
 __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char sm[];
+    // per-clip extrema of the CTA: {~bits(min), bits(max), warps arrived, -} per run of tiles of one
+    // clip; the consumer warps are never more than S <= 3 tiles apart, 8 entries never collide
+    __shared__ uint32_t s_mm[8][4];
     constexpr bool kMel = (MODE == FM_MEL);
     constexpr bool kFix = (EPI != 0);      // switches below are compile-time constants
     static_assert(!kFix || kMel, "fixed epilogues exist for the mel modes only");
@@ -217,6 +220,31 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const uint32_t slotB = slot_bytes(FR);
     unsigned char* slots = sm + off_slots(mel_taps, FR);
 
+    // ---- work claims of the producer warp (see there) ----
+    const int chunks16 = p.tile_stride >> 4;
+    const int CH = p.chunk, CM = p.chunk_mid, CT = p.chunk_tail;
+    const long long n_big = p.n_big, n_mid = p.n_mid;
+    auto claim_range = [&](long long q, int& len) -> long long {
+        if (q < n_big) { len = CH; return q * CH; }
+        q -= n_big;
+        if (q < n_mid) { len = CM; return n_big * CH + q * CM; }
+        len = CT;
+        return n_big * CH + n_mid * CM + (q - n_mid) * CT;
+    };
+    auto load_block = [&](int tile) -> int4 {
+        const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
+        return lane < chunks16 ? __ldg(reinterpret_cast<const int4*>(blk) + lane) : make_int4(0, 0, 0, 0);
+    };
+    // the block of the CTA's first tile is requested before the setup below, not after it
+    int len = 0;
+    long long first = 0;
+    int4 c_first = make_int4(0, 0, 0, 0);
+    if (warp == FR) {
+        cudaGridDependencySynchronize();   // the tile blocks come from the kernel in front (k_labels / k_tiles)
+        first = claim_range(blockIdx.x, len);
+        if (first < n_tiles) c_first = load_block(int(first));
+    }
+
     // ---- one-time setup: barriers, finite data in the stage buffers (the tables are loaded by the
     // consumer warps while the producer warp is already fetching the first tile) ----
     {
@@ -224,6 +252,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // frames the stage does not cover: they must hold finite numbers
         float4* z = reinterpret_cast<float4*>(slots);
         for (uint32_t i = tid; i < S * slotB / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 32) s_mm[tid >> 2][tid & 3] = 0u;
         if (tid == 0) {
             for (int s = 0; s < S; ++s) {
                 mbar_init(&full[s], 1);
@@ -247,7 +276,6 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // still in tile >= i - S - 1: kRing > S + 1 entries never collide.
         uint32_t slot = 0, phase = 0;
         const uint64_t pol_stream = l2_policy_evict_first();
-        const int chunks16 = p.tile_stride >> 4;
         // Work claims (launch_fused sets the schedule): claim q covers p.chunk consecutive tiles for
         // q < n_big, then p.chunk_mid tiles for n_mid claims, then p.chunk_tail tiles -- the chunks
         // shrink towards the end of the launch so that the CTAs finish within about one tile of each
@@ -256,33 +284,28 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // are issued when the LAST tile of the current claim starts: a CTA never owns more than one
         // chunk.  Consecutive tiles of a clip mostly stay on one SM (per-clip state changes rarely,
         // the row shared by two tiles is re-read one tile later).
-        const int CH = p.chunk, CM = p.chunk_mid, CT = p.chunk_tail;
-        const long long n_big = p.n_big, n_mid = p.n_mid;
-        auto claim_range = [&](long long q, int& len) -> long long {
-            if (q < n_big) { len = CH; return q * CH; }
-            q -= n_big;
-            if (q < n_mid) { len = CM; return n_big * CH + q * CM; }
-            len = CT;
-            return n_big * CH + n_mid * CM + (q - n_mid) * CT;
-        };
-        auto load_block = [&](int tile) -> int4 {
-            const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
-            return lane < chunks16 ? __ldg(reinterpret_cast<const int4*>(blk) + lane) : make_int4(0, 0, 0, 0);
-        };
         int i = 0;
-        int len = 0;
-        long long first = claim_range(blockIdx.x, len);
         if (lane == 0) IRIS_TRC(4);
         if (first < n_tiles) {
             int tile = int(first);
             int last = int(min((long long)n_tiles, first + len));
-            int4 c = load_block(tile);
+            int4 c = c_first;
             while (true) {
                 unsigned char* ent = sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes;
                 if (lane < chunks16) *reinterpret_cast<int4*>(ent + 16 * lane) = c;
                 __syncwarp();
                 const int n = __shfl_sync(0xffffffffu, c.x, 0);
                 const TileBlock* tb = reinterpret_cast<const TileBlock*>(ent);
+#ifdef IRIS_L2_PREFETCH   // measured on B200: cfg2 mel -1 us, cfg1 +2 us, min-max log-mel step +1.6 us (the prefetched lines compete with the mel rows kept for k_logmel_post): off
+                // The stages of this tile go out as stage buffers fall free, the later ones of a
+                // tile with more than S stages only one release + one DRAM round trip at a time:
+                // lane 2 + s holds StageDesc s of the block and asks L2 for its span right away.
+                {
+                    const uint32_t cnt = uint32_t(c.z) >> 16;   // StageDesc: {src.lo, src.hi, j_lo | j_cnt << 16, gain}
+                    const void* src = reinterpret_cast<const void*>((uint64_t(uint32_t(c.y)) << 32) | uint32_t(c.x));
+                    bulk_prefetch_l2_if(src, (cnt + 1u) * 2048u, lane >= 2 && lane < 2 + n && cnt != 0u);
+                }
+#endif
                 // look ahead: the block of the next tile of this claim is fetched while the stages of
                 // this one are issued; at the last tile of a claim the next claim goes out instead
                 const bool more = tile + 1 < last;
@@ -375,19 +398,36 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         // running per-clip extrema of this lane (flushed when the clip changes)
         float mn = __int_as_float(0x7f800000), mx = 0.f;
         int mm_clip = -1;
+        uint32_t mm_run = 0;   // runs of tiles of one clip this warp has flushed (the same sequence in every warp)
+        // The extrema of a run are combined in shared memory; the last of the FR warps to arrive sends
+        // the CTA's pair to the global scratch.  (One red.global pair per WARP and clip change --
+        // 81 k per 256-clip launch on 512 addresses -- measured 4 us of the kernel.)
         auto flush_minmax = [&]() {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
-#ifdef IRIS_EXP_NORED
-            const bool go = false;
-#else
-            const bool go = lane == 0 && mn <= mx;
-#endif
-            red_max_u32_if(&p.minmax[2 * mm_clip], ~__float_as_uint(mn), go);
-            red_max_u32_if(&p.minmax[2 * mm_clip + 1], __float_as_uint(mx), go);
+            if (lane == 0) {
+                uint32_t* sl = s_mm[mm_run & 7];
+                if (mn <= mx) {
+                    atomicMax(&sl[0], ~__float_as_uint(mn));
+                    atomicMax(&sl[1], __float_as_uint(mx));
+                }
+                __threadfence_block();
+                if (atomicAdd(&sl[2], 1u) == uint32_t(FR) - 1u) {
+                    __threadfence_block();
+                    const uint32_t a = *reinterpret_cast<volatile uint32_t*>(&sl[0]);
+                    const uint32_t c = *reinterpret_cast<volatile uint32_t*>(&sl[1]);
+                    *reinterpret_cast<volatile uint32_t*>(&sl[0]) = 0u;
+                    *reinterpret_cast<volatile uint32_t*>(&sl[1]) = 0u;
+                    *reinterpret_cast<volatile uint32_t*>(&sl[2]) = 0u;
+                    red_max_u32_if(&p.minmax[2 * mm_clip], a, (a | c) != 0u);
+                    red_max_u32_if(&p.minmax[2 * mm_clip + 1], c, (a | c) != 0u);
+                }
+            }
+            __syncwarp();
+            ++mm_run;
             mn = __int_as_float(0x7f800000);
             mx = 0.f;
         };
@@ -404,16 +444,42 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         uint32_t zbits = 0;
         int zb_clip = -1;
         const size_t clip_elems = size_t(p.n_mel) * p.T * C;
+#ifdef IRIS_TRACE
+        // where the time of a consumer warp goes (clock64 sums over its tiles): wait for the first
+        // stage of a tile, waits for the later stages, mix, FFT, epilogue
+        long long a_w0 = 0, a_w1 = 0, a_mix = 0, a_fft = 0, a_epi = 0, a_st = 0, c0, c1, c2, c3, c4 = 0;
+#define IRIS_ACC(dst, from, to) dst += (to) - (from)
+#else
+#define IRIS_ACC(dst, from, to) do { } while (0)
+#endif
         for (int i = 0;; ++i) {
             const TileBlock* tb = reinterpret_cast<const TileBlock*>(sm + OFF_RING + (i & (kRing - 1)) * kTileBlockBytes);
             // ---- gather + mix: v = sum over the stages of this tile of gain * frame ----
             cpx v[16];
+#ifdef IRIS_TRACE
+            c0 = clock64();
+            if (i > 0) IRIS_ACC(a_epi, c4, c0);
+#endif
             mbar_wait_parked(&full[slot], phase);           // also publishes the TileBlock of this tile
+#ifdef IRIS_TRACE
+            c1 = clock64();
+            IRIS_ACC(a_w0, c0, c1);
+#endif
+            // the rows of the first stage are requested before the tile header is looked at (the end
+            // marker's rows are stale but finite): the header's load-to-use latency hides behind them
+            {
+                const float2* src = reinterpret_cast<const float2*>(my_rows + slot * slotB);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 x = src[32 * q];
+                    v[q] = cpx{x.x, x.y};
+                }
+            }
             const int4 hdr = *reinterpret_cast<const int4*>(tb);
             const int n_st = hdr.x;
             if (i == 0 && tid == 0) IRIS_TRC(6);
 #ifdef IRIS_TRACE
-            if (tid == 0 && i > 0 && (i & 1) == 0 && (i >> 1) < 48) IRIS_TRC(16 + (i >> 1));   // tiles 0 .. i-1 done
+            if (tid == 0 && i > 0 && (i & 1) == 0 && (i >> 1) < 32) IRIS_TRC(16 + (i >> 1));   // tiles 0 .. i-1 done
             if (tid == 0 && i == 1) IRIS_TRC(7);
             if (tid == 0 && i == 21) IRIS_TRC(12);
 #endif
@@ -425,18 +491,21 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[0].j_lo);   // j_lo | j_cnt << 16, gain
                 const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
                 const float g0 = active ? __uint_as_float(dd.y) : 0.f;
-                const float2* src = reinterpret_cast<const float2*>(my_rows + slot * slotB);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float2 x = src[32 * q];
-                    v[q] = cscale(cpx{x.x, x.y}, g0);
-                }
+                for (int q = 0; q < 16; ++q) v[q] = cscale(v[q], g0);
                 __syncwarp();
                 mbar_arrive_if(&empty[slot], l0);
                 if (++slot == S) { slot = 0; phase ^= 1u; }
             }
             for (int e = 1; e < n_st; ++e) {
+#ifdef IRIS_TRACE
+                c2 = clock64();
+#endif
                 mbar_wait_parked(&full[slot], phase);
+#ifdef IRIS_TRACE
+                c3 = clock64();
+                IRIS_ACC(a_w1, c2, c3);
+#endif
                 const uint2 dd = *reinterpret_cast<const uint2*>(&tb->d[e].j_lo);
                 const bool active = unsigned(j - int(dd.x & 0xffffu)) < (dd.x >> 16);
                 if (active) {
@@ -454,6 +523,11 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             }
 
             if (tid == 0 && i == 21) IRIS_TRC(13);   // mix of tile 21 done
+#ifdef IRIS_TRACE
+            c2 = clock64();
+            IRIS_ACC(a_mix, c1, c2);
+            a_st += n_st;
+#endif
             const int b = hdr.y;
             const int pair = kFix ? 0 : (hdr.z >> 24);
             const int t = (hdr.z & 0xffffff) + j;
@@ -526,6 +600,10 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             }
 
             if (tid == 0 && i == 21) IRIS_TRC(14);   // FFT of tile 21 done
+#ifdef IRIS_TRACE
+            c4 = clock64();
+            IRIS_ACC(a_fft, c2, c4);
+#endif
             // ---- epilogue ----
             // register jj holds bin f = k1 + 16 (2 jj + par); its mirror 512 - f is register
             // 15 - jj of the partner lane (lane 0: its own register (16 - jj) & 15)
@@ -716,6 +794,13 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         }
         if (kMel && do_minmax && mm_clip >= 0) flush_minmax();
         if (tid == 0) { IRIS_TRC(8); IRIS_TR(10, tr_gtimer()); }
+#ifdef IRIS_TRACE
+        if (lane == 0 && (warp == 0 || warp == 5)) {
+            const int o = warp == 0 ? 48 : 54;
+            IRIS_TR(o, a_w0); IRIS_TR(o + 1, a_w1); IRIS_TR(o + 2, a_mix); IRIS_TR(o + 3, a_fft);
+            IRIS_TR(o + 4, a_epi); IRIS_TR(o + 5, a_st);
+        }
+#endif
     }
 }
 
@@ -736,7 +821,7 @@ int fused_pick_fr(int T, int mel_taps) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxFR) want = v;
     }
-    while (want > 1 && smem_total(mel_taps, want, FM_MEL, false) > 227u * 1024u) --want;
+    while (want > 1 && smem_total(mel_taps, want, FM_MEL, false) > 227u * 1024u - 256u) --want;
     (void)T;
     return want;
 }
@@ -836,7 +921,7 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
     if (all_tiles > 0x7fffffffLL || p.max_segs > kMaxStages || p.n_pairs > 127) return cudaErrorInvalidValue;
     if (mode == FM_MEL && (long long)p.n_mel * p.T * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;   // 32-bit row offsets inside a clip
     const size_t smem = fused_smem_bytes(p, mode);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 227 * 1024 - 256) return cudaErrorInvalidValue;   // (128 B of static shared memory: s_mm)
 #ifdef IRIS_TRACE
     trace_begin(p, num_sms, stream);
 #endif
@@ -858,9 +943,12 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
         static int per_sm = 1;                                                                  \
         static size_t per_sm_smem = 0;                                                          \
         if (attr_dev != dev) {                                                                  \
-            cudaError_t e = cudaFuncSetAttribute(k_fused<M, NJV, EPIV>,                               \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                                 227 * 1024);                                   \
+            cudaFuncAttributes fa;                                                              \
+            cudaError_t e = cudaFuncGetAttributes(&fa, k_fused<M, NJV, EPIV>);                  \
+            if (e != cudaSuccess) return e;                                                     \
+            e = cudaFuncSetAttribute(k_fused<M, NJV, EPIV>,                                     \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                     227 * 1024 - int(fa.sharedSizeBytes));                     \
             if (e != cudaSuccess) return e;                                                     \
             cudaFuncSetAttribute(k_fused<M, NJV, EPIV>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                  cudaSharedmemCarveoutMaxShared);                               \

@@ -79,6 +79,22 @@ ok = tr[:, 14] != 0
 print('tile 21 of a CTA, consumer warp 0 (us): wait+mix', q((tr[ok, 13] - tr[ok, 12]) / GHZ / 1e3))
 print('                                        fft     ', q((tr[ok, 14] - tr[ok, 13]) / GHZ / 1e3))
 print('                                        epilogue', q((tr[ok, 16 + 11] - tr[ok, 14]) / GHZ / 1e3))
+# where the time of a consumer warp goes (sums over all tiles of the CTA)
+for w, o in ((0, 48), (5, 54)):
+    a = tr[:, o:o + 6].astype(np.float64)
+    tiles = tr[:, 9].astype(np.float64)
+    tot = a[:, 0] + a[:, 2] + a[:, 3] + a[:, 4]
+    print('consumer warp %d, share of its time: wait first stage %.1f%%  wait later stages %.1f%%  mix %.1f%%  fft %.1f%%  '
+          'epilogue %.1f%%   (stages per tile %.2f)' % (w, 100 * a[:, 0].sum() / tot.sum(), 100 * a[:, 1].sum() / tot.sum(),
+          100 * (a[:, 2] - a[:, 1]).sum() / tot.sum(), 100 * a[:, 3].sum() / tot.sum(), 100 * a[:, 4].sum() / tot.sum(),
+          a[:, 5].sum() / tiles.sum()))
+    per = tot / tiles / GHZ / 1e3
+    fast = per < np.median(per)
+    for name, m in (('faster half of the CTAs', fast), ('slower half', ~fast)):
+        t = tot[m].sum()
+        print('   %-24s %.2f us per tile: wait0 %.1f%% wait+ %.1f%% mix %.1f%% fft %.1f%% epi %.1f%%' % (
+            name, per[m].mean(), 100 * a[m, 0].sum() / t, 100 * a[m, 1].sum() / t, 100 * (a[m, 2] - a[m, 1]).sum() / t,
+            100 * a[m, 3].sum() / t, 100 * a[m, 4].sum() / t))
 # first tiles: how long do tiles 0-1, 2-3 ... take
 for k in (1, 2, 3, 4):
     a = 7 if k == 1 else 16 + k - 1
