@@ -47,7 +47,7 @@ int build_tables(iris_ctx* c) {
     CU(cudaMemcpy(c->tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->ts.p, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->whalf.p, hann.data(), hann.size() * 4, cudaMemcpyHostToDevice));
-    CU(c->sched.reserve(8 * 64));     // (next chunk, CTAs finished) per launch of a split batch
+    CU(c->sched.reserve(8 * 64));     // (next chunk, CTAs finished) per launch of a split batch; [2], [3]: post tickets of an unsplit launch
     CU(cudaMemset(c->sched.p, 0, 8 * 64));
     return IRIS_OK;
 }
@@ -245,9 +245,15 @@ int run_logmel_minmax(iris_ctx* c, FusedParams& p, float* d_out, cudaStream_t st
     unsigned* done = reinterpret_cast<unsigned*>(mm + 2 * size_t(c->B));
     const int part = split_part_clips(c->B);
     if (part == 0) {
-        int rc = timed_fused(c, p, FM_MEL, st);
+        // fixed 2-channel instance: a post warp per CTA runs the second pass inside k_fused
+        int rc = prepare_fused(c, p, FM_MEL, c->max_segs);
         if (rc) return rc;
-        CU(launch_logmel_post(d_out, mm, done, c->B, per_clip, 1, 1, st));
+        p.clip_done = reinterpret_cast<uint32_t*>(done + c->B);
+        p.post_parts = p.clip_done + c->B;
+        p.post_in_kernel = fused_can_post_in_kernel(p) ? 1 : 0;
+        rc = timed_fused(c, p, FM_MEL, st);
+        if (rc) return rc;
+        if (!p.post_in_kernel) CU(launch_logmel_post(d_out, mm, done, c->B, per_clip, 1, 1, st));
         return IRIS_OK;
     }
     if (!c->aux) {
@@ -1108,7 +1114,7 @@ int iris_features_select(iris_ctx* c, int mode, int select, float* d_out, iris_s
         if (p.do_minmax) {   // per-clip (~min, max) bit patterns; k_logmel_post leaves them
                              // zeroed, so only a fresh allocation is cleared
             const void* before = c->minmax.p;
-            CU(c->minmax.reserve(size_t(c->B) * 12));   // [B,2] min/max words + [B] post counters
+            CU(c->minmax.reserve(size_t(c->B) * 20));   // [B,2] min/max words + [B] k_logmel_post counters + [B] tiles done + [B] parts posted
             if (c->minmax.p != before) CU(cudaMemsetAsync(c->minmax.p, 0, c->minmax.cap, st));
             p.minmax = c->minmax.as<uint32_t>();
         }

@@ -63,7 +63,7 @@ struct FusedParams {
     int32_t tile_first, tile_count;   // tiles [tile_first, tile_first + tile_count) of the batch belong to this launch
     int32_t seg_select;          // 0: every segment; 1: voices only; 2: background + noises only
                                  // (only_voice / only_noise of pipeline.py:37-38, 82-83, 104-108)
-    uint32_t* sched;             // [2] next chunk, CTAs finished; zero between launches
+    uint32_t* sched;             // [4] next chunk, CTAs finished, next post item, post warps finished; zero between launches
     // outputs
     float* out;             // layout depends on mode
     int32_t stage_out;      // spectrogram modes: store through the shared-memory staging area
@@ -73,6 +73,11 @@ struct FusedParams {
     // FM_MEL epilogue variants: log(x + 1e-8) and per-clip min-max before the log
     int32_t do_log, do_minmax;
     uint32_t* minmax;       // [B,2] atomicMax of (~bits(min), bits(max)); zeroed by k_tiles
+    // second pass inside k_fused (min-max log-mel, fixed 2-channel instance): consumer warps count the
+    // finished tiles of every clip, a post warp per CTA normalises + logs a clip as soon as it is whole
+    int32_t post_in_kernel;
+    uint32_t* clip_done;    // [B] tiles of the clip whose features are written (zero between launches)
+    uint32_t* post_parts;   // [B] parts of the clip the post warps have finished (zero between launches)
     // mel projection: filters are handled in rounds of 32 (m = lane + 32 r); every filter of
     // round r reads mel_L[r] consecutive magnitudes starting at bin mel_f_lo + mel_info[m]
     // (shorter filters are zero-padded), weights at mel_w[(row0(r) + i) * 32 + lane]
@@ -198,6 +203,11 @@ __device__ __forceinline__ void bulk_prefetch_l2_if(const void* src_gmem, uint32
         "@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src_gmem),
         "r"(bytes), "r"(uint32_t(pred))
         : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_f2_hint(float* addr, float a, float b, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(policy)

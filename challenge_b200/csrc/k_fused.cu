@@ -190,6 +190,23 @@ __device__ __forceinline__ void store_piece(const FusedParams& p, int b, int f, 
 // per-round flag branches, no odd-channel selects, C folded into the address arithmetic, the
 // projection loops unrolled to their 12 taps.  Measured: plain mel 202 -> 190 us.
 constexpr int EPI_MINMAX = 1, EPI_LOG = 2, EPI_C2 = 4;
+// EPI_POST (with EPI_MINMAX): the CTA carries one more warp that runs the second pass of the min-max
+// log-mel features -- (x - min) / max(max - min, 1e-8), log(. + 1e-8), data_utils.py:37-55 -- on every
+// clip as soon as its last tile is written, in kPostParts pieces handed out by a global ticket.  The
+// separate k_logmel_post launch (31 us behind a 173 us k_fused at 256 clips) disappears: the post
+// warps run in issue slots and L2 bandwidth the feature warps leave idle.
+constexpr int EPI_POST = 8;
+#ifndef IRIS_POST_PARTS
+#define IRIS_POST_PARTS 64   // 6.3 KB of a 400 KB clip per item: one round of 13 loads per lane (16 parts: 8-12 us per item in the tail)
+#endif
+#ifndef IRIS_POST_UNROLL
+#define IRIS_POST_UNROLL 13
+#endif
+#ifndef IRIS_POST_SLEEP
+#define IRIS_POST_SLEEP 1000
+#endif
+constexpr int kPostParts = IRIS_POST_PARTS;
+constexpr int kPostUnroll = IRIS_POST_UNROLL;
 #ifndef IRIS_FIX_FR
 #define IRIS_FIX_FR 8   // frames per tile of the fixed mel variants (experiment builds: 9 = 10 warps per CTA)
 #endif
@@ -200,10 +217,17 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     // per-clip extrema of the CTA: {~bits(min), bits(max), warps arrived, -} per run of tiles of one
     // clip; the consumer warps are never more than S <= 3 tiles apart, 8 entries never collide
     __shared__ uint32_t s_mm[8][4];
+    // kPost: {clip, tiles} of the run in entry r & 7, the generation of every entry (bumped by the post
+    // warp when it has published the run and the entry may be reused) and the consumer warps that have
+    // left the tile loop
+    __shared__ uint32_t s_run[8][2];
+    __shared__ uint32_t s_gen[8];
+    __shared__ uint32_t s_exit;
     constexpr bool kMel = (MODE == FM_MEL);
     constexpr bool kFix = (EPI != 0);      // switches below are compile-time constants
     static_assert(!kFix || kMel, "fixed epilogues exist for the mel modes only");
     constexpr int S = slots_of(MODE);      // stage buffers
+    constexpr bool kPost = kFix && (EPI & EPI_POST) && (EPI & EPI_MINMAX);
     const bool do_minmax = kFix ? bool(EPI & EPI_MINMAX) : (p.do_minmax != 0);
     const bool do_lg = kFix ? bool(EPI & EPI_LOG) : (p.do_log && !p.do_minmax);
     const int C = kFix ? 2 : p.C;
@@ -253,6 +277,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         float4* z = reinterpret_cast<float4*>(slots);
         for (uint32_t i = tid; i < S * slotB / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < 32) s_mm[tid >> 2][tid & 3] = 0u;
+        if (tid < 8) s_gen[tid] = 0u;
+        if (tid == 0) s_exit = 0u;
         if (tid == 0) {
             for (int s = 0; s < S; ++s) {
                 mbar_init(&full[s], 1);
@@ -268,6 +294,147 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     // zeroed extrema scratch are visible from here on
     cudaGridDependencySynchronize();
     if (tid == 0) IRIS_TRC(3);
+
+    // ---- second pass (kPost): the post warp of the CTA from the start, the consumer warps once they
+    // have run out of tiles ----
+    // Runs of tiles of one clip that the FR consumer warps of this CTA have all finished are published
+    // by the POST warp: it sends the run's extrema to the global scratch and, behind ONE device-scope
+    // fence, adds its tiles to the clip's count.  (With the fence in the consumer warp that arrived last
+    // the kernel took 204 us instead of 173: the warp stalls on the fence and the stage ring stalls
+    // with it.)  Only lane 0 of the post warp calls this.
+    uint32_t run_tail = 0;
+    auto service_runs = [&]() {
+        while (true) {
+            uint32_t* sl = s_mm[run_tail & 7];
+            if (*reinterpret_cast<volatile uint32_t*>(&sl[2]) != uint32_t(FR)) break;
+            __threadfence_block();
+            const uint32_t a = *reinterpret_cast<volatile uint32_t*>(&sl[0]);
+            const uint32_t c = *reinterpret_cast<volatile uint32_t*>(&sl[1]);
+            const uint32_t clip = *reinterpret_cast<volatile uint32_t*>(&s_run[run_tail & 7][0]);
+            const uint32_t tiles = *reinterpret_cast<volatile uint32_t*>(&s_run[run_tail & 7][1]);
+            *reinterpret_cast<volatile uint32_t*>(&sl[0]) = 0u;
+            *reinterpret_cast<volatile uint32_t*>(&sl[1]) = 0u;
+            *reinterpret_cast<volatile uint32_t*>(&sl[2]) = 0u;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&s_gen[run_tail & 7]) = (run_tail >> 3) + 1u;   // entry free for run + 8
+            red_max_u32_if(&p.minmax[2 * clip], a, (a | c) != 0u);
+            red_max_u32_if(&p.minmax[2 * clip + 1], c, (a | c) != 0u);
+            __threadfence();
+            atomicAdd(&p.clip_done[clip], tiles);
+            ++run_tail;
+        }
+    };
+    // own_runs: the caller is the post warp (it also publishes the runs of its CTA while it waits and works)
+    auto post_loop = [&](const bool own_runs) {
+#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 3   // timing experiment: the post warps only publish runs, k_logmel_post is missing
+        if (own_runs) {
+            if (lane == 0) {
+                while (*reinterpret_cast<volatile uint32_t*>(&s_exit) != uint32_t(FR)) {
+                    service_runs();
+                    __nanosleep(64);
+                }
+                service_runs();
+            }
+        }
+        return;
+#endif
+        // items = (clip, part) in clip order; a clip is whole when clip_done reaches its tile count
+        const uint32_t tpc = uint32_t((p.T + FR - 1) / FR) * uint32_t(p.n_pairs);
+        const size_t clip_elems = size_t(p.n_mel) * p.T * C;
+        const uint32_t n4 = uint32_t(clip_elems >> 2);   // float4 per clip (the launcher checks clip_elems % 4 == 0)
+        const uint32_t n_items = uint32_t(p.B) * kPostParts;
+#ifdef IRIS_TRACE
+        long long pw = 0, pp = 0, pn = 0, pt0 = clock64();
+#endif
+        while (true) {
+            uint32_t t = 0;
+            if (lane == 0) {
+                if (own_runs) service_runs();
+                t = atomicAdd(&p.sched[2], 1u);
+            }
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= n_items) break;
+            const uint32_t b = t / kPostParts, part = t - b * kPostParts;
+#ifdef IRIS_TRACE
+            const long long q0 = clock64();
+#endif
+            if (lane == 0)
+                while (ld_acquire_gpu_u32(&p.clip_done[b]) < tpc) {
+                    if (own_runs) service_runs();   // (the clip may be waiting for a run of this very CTA)
+                    __nanosleep(IRIS_POST_SLEEP);
+                }
+            __syncwarp();
+#ifdef IRIS_TRACE
+            const long long q1 = clock64();
+            pw += q1 - q0;
+#endif
+            const float mn = __uint_as_float(~__ldcg(&p.minmax[2 * b]));
+            const float mx = __uint_as_float(__ldcg(&p.minmax[2 * b + 1]));
+            const float inv = 1.f / fmaxf(mx - mn, 1e-8f);
+            float4* v = reinterpret_cast<float4*>(p.out + size_t(b) * clip_elems);
+            const uint32_t lo = uint32_t((uint64_t(n4) * part) / kPostParts);
+            const uint32_t hi = uint32_t((uint64_t(n4) * (part + 1)) / kPostParts);
+#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 1   // timing experiment: synchronisation only
+            if (false)
+#endif
+            for (uint32_t i0 = lo + lane; i0 < hi; i0 += 32 * kPostUnroll) {
+                float4 a[kPostUnroll];
+#pragma unroll
+                for (int u = 0; u < kPostUnroll; ++u)
+                    if (i0 + 32 * u < hi) a[u] = __ldcg(v + i0 + 32 * u);
+#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 2   // timing experiment: loads only
+                float acc = 0.f;
+#pragma unroll
+                for (int u = 0; u < kPostUnroll; ++u)
+                    if (i0 + 32 * u < hi) acc += a[u].x + a[u].y + a[u].z + a[u].w;
+                if (acc == 1.2345e-30f) v[i0] = a[0];
+                continue;
+#endif
+#pragma unroll
+                for (int u = 0; u < kPostUnroll; ++u)
+                    if (i0 + 32 * u < hi) {
+                        // same arithmetic as k_logmel_post (k_post.cu): x - min first
+                        a[u].x = __logf(fmaf(a[u].x - mn, inv, 1e-8f));
+                        a[u].y = __logf(fmaf(a[u].y - mn, inv, 1e-8f));
+                        a[u].z = __logf(fmaf(a[u].z - mn, inv, 1e-8f));
+                        a[u].w = __logf(fmaf(a[u].w - mn, inv, 1e-8f));
+                        v[i0 + 32 * u] = a[u];
+                    }
+                if (own_runs && lane == 0) service_runs();
+            }
+            __syncwarp();
+#ifdef IRIS_TRACE
+            pp += clock64() - q1;
+            ++pn;
+#endif
+            // the last part of a clip leaves its scratch zeroed for the next launch
+            if (lane == 0 && atomicAdd(&p.post_parts[b], 1u) == kPostParts - 1) {
+                p.minmax[2 * b] = 0u;
+                p.minmax[2 * b + 1] = 0u;
+                p.clip_done[b] = 0u;
+                p.post_parts[b] = 0u;
+            }
+        }
+#ifdef IRIS_TRACE
+        if (lane == 0 && warp == FR + 1) { IRIS_TR(60, pw); IRIS_TR(61, pp); IRIS_TR(62, pn); IRIS_TR(63, clock64() - pt0); }
+        if (lane == 0 && warp == 0) { IRIS_TR(15, pn); IRIS_TR(12, pp); IRIS_TR(13, pw); }
+#endif
+        if (own_runs) {   // the consumer warps may still be at their last tiles: publish until all have left
+            if (lane == 0) {
+                while (*reinterpret_cast<volatile uint32_t*>(&s_exit) != uint32_t(FR)) {
+                    service_runs();
+                    __nanosleep(64);
+                }
+                __threadfence_block();
+                service_runs();
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && atomicAdd(&p.sched[3], 1u) == gridDim.x * uint32_t(FR + 1) - 1u) {   // last warp of the grid
+            p.sched[2] = 0u;
+            p.sched[3] = 0u;
+        }
+    };
 
     if (warp == FR) {
         // =========================== producer warp ===========================
@@ -366,6 +533,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 }
             }
         }
+    } else if (kPost && warp == FR + 1) {
+        post_loop(true);
     } else {
         // =========================== consumer warps ===========================
         {
@@ -399,6 +568,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         float mn = __int_as_float(0x7f800000), mx = 0.f;
         int mm_clip = -1;
         uint32_t mm_run = 0;   // runs of tiles of one clip this warp has flushed (the same sequence in every warp)
+        uint32_t mm_tiles = 0; // tiles of the current run (kPost)
         // The extrema of a run are combined in shared memory; the last of the FR warps to arrive sends
         // the CTA's pair to the global scratch.  (One red.global pair per WARP and clip change --
         // 81 k per 256-clip launch on 512 addresses -- measured 4 us of the kernel.)
@@ -408,14 +578,23 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
+            __syncwarp();   // (kPost: the feature stores of all lanes are ordered before lane 0's fences)
             if (lane == 0) {
                 uint32_t* sl = s_mm[mm_run & 7];
+                if (kPost) {
+                    // the entry is free once the post warp has published the run that used it 8 runs ago
+                    // (it always has, unless the post warp fell far behind)
+                    while (*reinterpret_cast<volatile uint32_t*>(&s_gen[mm_run & 7]) != (mm_run >> 3)) __nanosleep(32);
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&s_run[mm_run & 7][0]) = uint32_t(mm_clip);   // (the same
+                    *reinterpret_cast<volatile uint32_t*>(&s_run[mm_run & 7][1]) = mm_tiles;            // in every warp)
+                }
                 if (mn <= mx) {
                     atomicMax(&sl[0], ~__float_as_uint(mn));
                     atomicMax(&sl[1], __float_as_uint(mx));
                 }
                 __threadfence_block();
-                if (atomicAdd(&sl[2], 1u) == uint32_t(FR) - 1u) {
+                if (atomicAdd(&sl[2], 1u) == uint32_t(FR) - 1u && !kPost) {
                     __threadfence_block();
                     const uint32_t a = *reinterpret_cast<volatile uint32_t*>(&sl[0]);
                     const uint32_t c = *reinterpret_cast<volatile uint32_t*>(&sl[1]);
@@ -428,6 +607,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             }
             __syncwarp();
             ++mm_run;
+            mm_tiles = 0;
             mn = __int_as_float(0x7f800000);
             mx = 0.f;
         };
@@ -616,6 +796,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                     if (mm_clip >= 0) flush_minmax();
                     mm_clip = b;
                 }
+                if (kPost) ++mm_tiles;
                 // (|ch0|, |ch1|) of every bin the lane holds, indexed by the bin itself (at most 257 x 8 B
                 // of the warp's 4352-byte exchange rows): no range checks on the way in
                 float2* mg = reinterpret_cast<float2*>(xch);
@@ -794,6 +975,14 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         }
         if (kMel && do_minmax && mm_clip >= 0) flush_minmax();
         if (tid == 0) { IRIS_TRC(8); IRIS_TR(10, tr_gtimer()); }
+        if (kPost) {   // out of tiles: help with the clips that are still to be normalised
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&s_exit, 1u);
+            }
+            post_loop(false);
+        }
 #ifdef IRIS_TRACE
         if (lane == 0 && (warp == 0 || warp == 5)) {
             const int o = warp == 0 ? 48 : 54;
@@ -802,6 +991,21 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         }
 #endif
     }
+}
+
+// the second pass runs inside k_fused for the fixed 2-channel min-max instance (launch_fused picks it
+// under the same conditions) when a clip is a whole number of float4
+bool fused_can_post_in_kernel(const FusedParams& p) {
+    // Opt-in (IRIS_POST_IN_KERNEL=1).  Measured on B200, cfg2, 256 clips (profiles/r02_post_in_kernel.txt):
+    // the kernel grows from 173 to 196 us (run publishing +7, tickets and waits +5, the loads +5,
+    // arithmetic and stores +5 us) while k_logmel_post alone takes 29 us and hides the metric leg
+    // (10 us) behind it: the step is 231 us either way, so the separate pass stays the default.
+    static const bool on = getenv("IRIS_POST_IN_KERNEL") && atoi(getenv("IRIS_POST_IN_KERNEL")) != 0;
+    if (!on || getenv("IRIS_NO_FIXED_EPI")) return false;
+    return p.do_minmax && p.C == 2 && p.mel_f_lo + p.mel_f_n <= 128 && p.mel_L[0] == fixed_mel_L(0) &&
+           p.mel_L[1] == fixed_mel_L(1) && p.mel_L[2] == fixed_mel_L(2) && p.mel_L[3] == fixed_mel_L(3) &&
+           p.l2_hints && p.fr == IRIS_FIX_FR && p.mel_taps == 12 && ((size_t(p.n_mel) * p.T * p.C) & 3) == 0 &&
+           p.tile_first == 0 && p.tile_count == 0;
 }
 
 size_t fused_smem_bytes(const FusedParams& p, int mode) { return smem_total(p.mel_taps, p.fr, mode, p.stage_out != 0); }
@@ -927,7 +1131,6 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
 #endif
     if (what & FUSED_LAUNCH_TILES) k_tiles<<<unsigned((all_tiles + 127) / 128), 128, 0, stream>>>(p);
     if (!(what & FUSED_LAUNCH_KERNEL)) return cudaGetLastError();
-    const int threads = (FR + 1) * 32;
     // programmatic dependent launch behind k_tiles of the same call (prologue overlap); a launch on
     // its own (later part of a split batch) is an ordinary one
     const int pdl = (what & (FUSED_LAUNCH_TILES | FUSED_LAUNCH_PDL)) && !getenv("IRIS_NO_PDL") ? 1 : 0;
@@ -939,6 +1142,7 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
     // registers are granted per warp in larger units) -- 4-ch COMPLEX 570 -> 730 us, mel 200 -> 265 us.
 #define IRIS_LAUNCH(M, NJV, EPIV)                                                                     \
     {                                                                                           \
+        const int threads = (FR + 1 + (((EPIV) & EPI_POST) ? 1 : 0)) * 32;                      \
         static int attr_dev = -1;   /* function attributes are per device */                    \
         static int per_sm = 1;                                                                  \
         static size_t per_sm_smem = 0;                                                          \
@@ -994,6 +1198,7 @@ cudaError_t launch_fused(const FusedParams& p_in, int mode, int num_sms, cudaStr
                      p.mel_L[2] != fixed_mel_L(2) || p.mel_L[3] != fixed_mel_L(3) ||
                      !p.l2_hints || FR != IRIS_FIX_FR || p.mel_taps != 12 || getenv("IRIS_NO_FIXED_EPI"))
                 IRIS_LAUNCH(FM_MEL, 4, 0)
+            else if (p.do_minmax && p.post_in_kernel) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_MINMAX | EPI_POST)
             else if (p.do_minmax) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_MINMAX)
             else if (p.do_log) IRIS_LAUNCH(FM_MEL, 4, EPI_C2 | EPI_LOG)
             else IRIS_LAUNCH(FM_MEL, 4, EPI_C2)

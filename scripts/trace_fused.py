@@ -95,6 +95,11 @@ for w, o in ((0, 48), (5, 54)):
         print('   %-24s %.2f us per tile: wait0 %.1f%% wait+ %.1f%% mix %.1f%% fft %.1f%% epi %.1f%%' % (
             name, per[m].mean(), 100 * a[m, 0].sum() / t, 100 * a[m, 1].sum() / t, 100 * (a[m, 2] - a[m, 1]).sum() / t,
             100 * a[m, 3].sum() / t, 100 * a[m, 4].sum() / t))
+if tr[:, 62].any():
+    print('post warp of a CTA: items', q(tr[:, 62]), '\n   us waiting for clips', q(tr[:, 60] / GHZ / 1e3),
+          '\n   us normalising     ', q(tr[:, 61] / GHZ / 1e3), '\n   us alive           ', q(tr[:, 63] / GHZ / 1e3))
+    print('   us per item', q(tr[:, 61] / np.maximum(tr[:, 62], 1) / GHZ / 1e3))
+    print('consumer warp 0 after its tiles: items', q(tr[:, 15]), ' us normalising', q(tr[:, 12] / GHZ / 1e3), ' us waiting', q(tr[:, 13] / GHZ / 1e3))
 # first tiles: how long do tiles 0-1, 2-3 ... take
 for k in (1, 2, 3, 4):
     a = 7 if k == 1 else 16 + k - 1
