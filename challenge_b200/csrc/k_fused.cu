@@ -151,6 +151,8 @@ __device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float 
         r0 *= filt; i0 *= filt; r1 *= filt; i1 *= filt;
     }
     float a0 = r0, a1 = r1, b0 = i0, b1 = i1;
+    // (a short cut for masked cells -- |.| = +0, atan2(+-0, +-0) from the sign bits -- was measured on
+    // B200: 4-ch MAGPHASE 678.7 -> 685.0 us; the branch costs more than the polynomial it skips)
     if (MODE != FM_COMPLEX) {
         a0 = sqrt_approx(fmaf(r0, r0, i0 * i0));   // transforms.py:116
         a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));

@@ -27,6 +27,57 @@ def phase_err(mag_ref, ph, ph_ref, gate=1e-3):
     return float(np.abs(d[sel]).max()) if sel.any() else 0.0
 
 
+def rel_err_gated(a, b, gate=1e-3):
+    """Element-wise relative error max|a-b| / |b| over the cells with |b| > gate * max|b| (below the
+    gate an absolute fp32 error of ~3e-7 max|b| is more than gate^-1 * 3e-7 relative: ill-posed)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    sel = np.abs(b) > gate * np.abs(b).max()
+    return float((np.abs(a - b)[sel] / np.abs(b)[sel]).max()) if sel.any() else 0.0
+
+
+def phase_report(mag_ref, ph, ph_ref):
+    """The phase figures SURVEY.md 8d asks for.  An absolute error e of re / im (fp32 FFT rounding,
+    ~1e-6 of max|X| on both sides) turns into a phase error e / |X|, so the circular error is
+    reported by magnitude gate, together with the magnitude-weighted error |dphi| |X| / max|X| over
+    ALL cells (the complex-domain error the phase error stands for), the branch-cut sign mismatches
+    (ref and got on opposite sides of +-pi: |raw difference| > pi) among the gated cells, and the
+    cells of exactly zero magnitude (masked: atan2(+-0, +-0) is decided by sign bits alone) whose
+    phase is not bit-identical."""
+    mag_ref = np.asarray(mag_ref, np.float64)
+    ph = np.asarray(ph, np.float64)
+    ph_ref = np.asarray(ph_ref, np.float64)
+    raw = ph - ph_ref
+    d = np.abs(np.angle(np.exp(1j * raw)))
+    mx = mag_ref.max()
+    out = {}
+    for name, gate in (('gate1e-3', 1e-3), ('gate1e-2', 1e-2), ('gate1e-1', 1e-1)):
+        sel = mag_ref > gate * mx
+        out[name] = float(d[sel].max()) if sel.any() else 0.0
+    out['weighted'] = float((d * mag_ref).max() / mx)
+    sel = mag_ref > 1e-3 * mx
+    out['cut_flips_gated'] = int((np.abs(raw[sel]) > np.pi).sum())
+    out['cut_flips_all'] = int((np.abs(raw) > np.pi).sum())
+    zero = mag_ref == 0
+    out['zero_cells'] = int(zero.sum())
+    out['zero_cells_differ'] = int(((ph[zero] != ph_ref[zero]) | (np.signbit(ph[zero]) != np.signbit(ph_ref[zero]))).sum())
+    return out
+
+
+def logmag_report(lg, lg_ref):
+    """log(|X| + 1e-8) features: absolute error of the log by magnitude gate (an absolute error e of
+    |X| is e / |X| in the log) and the normalised max error back in the linear domain."""
+    lg = np.asarray(lg, np.float64)
+    lg_ref = np.asarray(lg_ref, np.float64)
+    m, m_ref = np.exp(lg), np.exp(lg_ref)
+    out = {}
+    for name, gate in (('gate1e-3', 1e-3), ('gate1e-2', 1e-2), ('gate1e-1', 1e-1)):
+        sel = m_ref > gate * m_ref.max()
+        out[name] = float(np.abs(lg[sel] - lg_ref[sel]).max()) if sel.any() else 0.0
+    out['linear_nmax'] = float(np.abs(m - m_ref).max() / m_ref.max())
+    return out
+
+
 @pytest.fixture(scope='session')
 def engine():
     import torch

@@ -160,8 +160,21 @@ def test_minmax_log_labels_and_remaps(mods):
     assert np.array_equal(_np(D.stft_filter(3)(spec)), OD.stft_filter(3)(spec))
     _, got = D.multiply_label(3.0)(None, y)
     assert np.array_equal(_np(got), y * 3)
+    # speech_enhancement_preprocess (data_utils.py:139-148): values, incl. the quirk that the
+    # only_voice / only_noise spectrograms are cut with the width of the ALREADY halved x
     x2 = D.speech_enhancement_preprocess(spec)
-    assert _np(x2).shape == (256, 20, 2)
+    assert _np(x2).shape == (256, 20, 2) and np.array_equal(_np(x2), OD.speech_enhancement_preprocess(spec))
+    rng_se = np.random.default_rng(12)
+    lab_v = (rng_se.random((5, 20, 3)) < 0.3).astype(np.float32)
+    ov = rng_se.standard_normal(spec.shape).astype(np.float32)
+    on = rng_se.standard_normal(spec.shape).astype(np.float32)
+    gx, gy = D.speech_enhancement_preprocess(spec, (lab_v, ov, on))
+    rx, ry = OD.speech_enhancement_preprocess(spec, (lab_v, ov, on))
+    assert np.array_equal(_np(gx), rx)
+    assert len(gy) == len(ry) == 3
+    for g, r in zip(gy, ry):
+        assert _np(g).shape == r.shape and np.array_equal(_np(g), r)
+    assert ry[0].shape == (20, 3) and ry[1].shape == (256, 20, 1)
     specs, labels = D.augment(spec, 'y')
     assert labels == 'y' and _np(specs).shape == spec.shape
 

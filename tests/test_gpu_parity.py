@@ -5,11 +5,40 @@ labels / keep flags / metric counts; float features within normalised max error 
 import numpy as np
 import pytest
 
-from conftest import nmax_err, phase_err
+from conftest import logmag_report, nmax_err, phase_err, phase_report, rel_err_gated
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
+# Phase and log-magnitude bars.  Both sides run the FFT in fp32, so re / im carry an absolute error
+# of ~3e-7 of max|X| and a cell of magnitude m has a phase (and log-magnitude) error of ~3e-7 max / m:
+# measured on B200 (scripts/parity_report.py, cfg3 shape, three draws) 4.1e-5 .. 8.4e-5 rad and
+# 5.8e-5 .. 8.9e-5 in the log at the 1e-3 gate, 1.0e-5 at a 1e-2 gate, 2.7e-7 magnitude-weighted.
+PHASE_TOL = 2e-4          # rad, cells with |X| > 1e-3 max|X|
+PHASE_WEIGHTED_TOL = 2e-6  # |dphi| |X| / max|X|, every cell
+LOGMAG_TOL = 2e-4         # |d log|, cells with |X| > 1e-3 max|X|
+NOISE = 2e-6              # of max|X|: an imaginary part below this has no resolvable sign
+
+
+def _check_phase(mag_ref, ph, ph_ref, c_got=None, c_ref=None):
+    """circular phase error by magnitude gate + the count of +-pi sign mismatches.
+    A mismatch is only legitimate where the imaginary part is rounding noise on both sides (e.g.
+    the reflect-padded edge frames, whose spectrum is real up to rounding); cells of exactly zero
+    magnitude (masked) must agree up to the signs of noise-level components."""
+    r = phase_report(mag_ref, ph, ph_ref)
+    assert r['gate1e-3'] < PHASE_TOL, r
+    assert r['weighted'] < PHASE_WEIGHTED_TOL, r
+    C = mag_ref.shape[-1]
+    if c_got is not None:
+        raw = ph.astype(np.float64) - ph_ref
+        flips = np.abs(raw) > np.pi
+        mx = np.abs(c_ref).max()
+        im_g, im_r = np.abs(c_got[..., C:][flips]), np.abs(c_ref[..., C:][flips])
+        assert (im_g <= NOISE * mx).all() and (im_r <= NOISE * mx).all(), (r, im_g.max(), im_r.max())
+    if r['zero_cells']:
+        assert r['zero_cells_differ'] <= 2e-3 * r['zero_cells'] + 8, r
+    return r
+
 
 
 def _draw(w, B, T, C_remap=0, seed=0, masks=True, V=7, M=2, min_ratio=1, merge_extra=0):
@@ -118,17 +147,20 @@ def test_cfg3_four_channel_magphase_labels(engine, workload_factory):
     got = engine.features(L.FEAT_MAGPHASE).cpu().numpy()
     assert got.shape == ref.shape == (4, 257, 626, 8)
     assert nmax_err(got[..., :4], ref[..., :4]) < TOL
-    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    assert rel_err_gated(got[..., :4], ref[..., :4]) < 5e-4       # element-wise, |X| > 1e-3 max|X|
     got_c = engine.features(L.FEAT_COMPLEX).cpu().numpy()     # both channel pairs stored as 32-byte cells
     ref_c = _oracle(w, d, mode='complex')[0]
     assert got_c.shape == ref_c.shape == (4, 257, 626, 8)
     assert nmax_err(got_c, ref_c) < TOL
+    rep = _check_phase(ref[..., :4], got[..., 4:], ref[..., 4:], got_c, ref_c)
+    print('cfg3 phase report:', rep)
     for ch in range(8):                                       # every channel lands in its own column
         assert nmax_err(got_c[..., ch], ref_c[..., ch]) < 10 * TOL, ch
     got = engine.features(L.FEAT_LOG_MAGPHASE).cpu().numpy()
     ref = _oracle(w, d, mode='log_magphase')[0]
-    sel = ref[..., :4] > np.log(1e-3 * np.exp(ref[..., :4].max()))
-    assert np.abs(got[..., :4][sel] - ref[..., :4][sel]).max() < 1e-2
+    lr = logmag_report(got[..., :4], ref[..., :4])
+    assert lr['linear_nmax'] < TOL and lr['gate1e-3'] < LOGMAG_TOL, lr
+    assert phase_report(np.exp(ref[..., :4]), got[..., 4:], ref[..., 4:])['gate1e-3'] < PHASE_TOL   # phase passes through
     got = engine.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy()
     assert nmax_err(got, _oracle(w, d, mode='logmel_minmax')[0]) < TOL
 
@@ -187,7 +219,7 @@ def test_channel_remaps_and_filter(engine, workload_factory):
     ref = _oracle(w, d, mode='magphase', remap='merge_aug', n_out_chan=4)[0]
     assert got.shape == ref.shape == (3, 257, 200, 8)
     assert nmax_err(got[..., :4], ref[..., :4]) < TOL
-    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    _check_phase(ref[..., :4], got[..., 4:], ref[..., 4:])
 
 
 def test_empty_offset_range_raises_like_reference(engine, workload_factory):
@@ -293,9 +325,11 @@ def test_full_size_properties_cfg2(engine, workload_factory):
     kp = keep.cpu().numpy()
     assert np.all(kp[:, 0] == 1)          # the first voice can never collide
     assert not kp[np.arange(7)[None, :] >= d.n_voices[:, None]].any()
-    clips = [0, 101, 255]
+    clips = sorted(set([0, 255] + np.random.default_rng(7).choice(B, 32, replace=False).tolist()))
     ref, ref_y, _, ref_keep = _oracle(w, d, mode='logmel_minmax', clips=clips)
     assert nmax_err(xn[clips], ref) < TOL
+    for i, b in enumerate(clips):                     # every clip on its own scale
+        assert nmax_err(xn[b], ref[i]) < TOL, b
     assert np.array_equal(fr[clips], ref_y)
     assert np.array_equal(kp[clips], np.stack(ref_keep))
 
@@ -326,11 +360,13 @@ def test_full_size_cfg3_four_channel_1024(engine, workload_factory):
     fr = frame.cpu().numpy()
     kp = keep.cpu().numpy()
     assert set(np.unique(fr)) <= {0.0, 1.0} and np.all(kp[:, 0] == 1)
-    clips = [0, 511, 1023]
+    clips = sorted(set([0, 1023] + np.random.default_rng(8).choice(B, 32, replace=False).tolist()))
     ref, ref_y, _, ref_keep = _oracle(w, d, mode='magphase', clips=clips)
     got = x[clips].cpu().numpy()
     assert nmax_err(got[..., :4], ref[..., :4]) < TOL
-    assert phase_err(ref[..., :4], got[..., 4:], ref[..., 4:]) < 1e-3
+    for i, b in enumerate(clips):
+        assert nmax_err(got[i, ..., :4], ref[i, ..., :4]) < TOL, b
+    _check_phase(ref[..., :4], got[..., 4:], ref[..., 4:])
     assert np.array_equal(fr[clips], ref_y)
     assert np.array_equal(kp[clips], np.stack(ref_keep))
 
@@ -363,6 +399,13 @@ def test_full_size_cfg4_shards_equal_the_whole_batch(engine, workload_factory):
         assert torch.equal(t_r, triples[lo:hi]), r
         total += c_r
     assert torch.equal(total, tpfpfn)
+    clips = sorted(np.random.default_rng(9).choice(B, 32, replace=False).tolist())   # parity on 32 random clips
+    ref, ref_y, _, ref_keep = _oracle(w, d, mode='logmel_minmax', clips=clips)
+    got = x[clips].cpu().numpy()
+    for i, b in enumerate(clips):
+        assert nmax_err(got[i], ref[i]) < TOL, b
+    assert np.array_equal(frame[clips].cpu().numpy(), ref_y)
+    assert np.array_equal(keep[clips].cpu().numpy(), np.stack(ref_keep))
     xn = x[::1024].cpu().numpy()                       # every clip spans [log 1e-8, log(1 + 1e-8)]
     assert np.allclose(xn.reshape(len(xn), -1).min(1), np.log(np.float32(1e-8)), rtol=0, atol=1e-5)
     assert np.allclose(xn.reshape(len(xn), -1).max(1), 0, atol=1e-6)

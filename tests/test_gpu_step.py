@@ -1,6 +1,8 @@
 """GPU tests of the one-call batch step (iris_step), the DLPack hand-over, per-pipeline bank
 sets and the tf.data surface of IrisDataset -- all through the C ABI, checked against the CPU
 oracle on the draws the step itself made (iris_step_draws)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -275,3 +277,45 @@ def test_nccl_count_allreduce_two_ranks():
                         os.path.join(root, 'tests', 'nccl_worker.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'NCCL_WORKER_OK' in r.stdout
+
+
+def test_second_pass_inside_k_fused_is_bit_identical(engine, workload_factory, tmp_path):
+    """IRIS_POST_IN_KERNEL=1 (opt-in experiment, k_fused.cu EPI_POST): a post warp per CTA runs
+    minmax + log_on_mel (data_utils.py:37-55) inside k_fused instead of the k_logmel_post launch.
+    Same arithmetic on the same extrema: the features must be bit-identical, call after call (the
+    per-clip scratch is re-zeroed by the kernel itself)."""
+    import subprocess
+    import sys
+    from challenge_b200 import _lib as L
+    w = workload_factory(2)
+    engine.set_mel(80)       # (an earlier test leaves a wider matrix on the shared engine)
+    from challenge_b200.plan import draw_batch
+    d = draw_batch(np.random.default_rng(77), 24, 626, w.bg_frames, w.voice_frames, w.noise_frames, max_voices=7,
+                   max_noises=2, snr=-20, min_ratio=1, n_time_masks=6, n_freq_masks=1)
+    engine.upload_plan(d)
+    engine.labels()
+    ref = engine.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy()
+    out = tmp_path / 'post.npy'
+    code = '''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from challenge_b200 import _lib as L
+from challenge_b200.engine import Engine
+from challenge_b200.plan import draw_batch
+from challenge_b200.synth import synthetic_banks
+eng = Engine(0); eng.set_mel(80)
+bgs, voices, labels, noises = synthetic_banks(20202, 2, n_bg=4, n_voice=24, n_noise=6, bg_seconds=10.0)
+bf = eng.register_bank(L.BANK_BG, bgs); vf = eng.register_bank(L.BANK_VOICE, voices, labels=labels)
+nf = eng.register_bank(L.BANK_NOISE, noises)
+d = draw_batch(np.random.default_rng(77), 24, 626, bf, vf, nf, max_voices=7, max_noises=2, snr=-20, min_ratio=1,
+               n_time_masks=6, n_freq_masks=1)
+eng.upload_plan(d); eng.labels()
+a = eng.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy()
+b = eng.features(L.FEAT_LOGMEL_MINMAX).cpu().numpy()
+assert np.array_equal(a, b), 'second call differs'
+np.save(%r, b)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(out))
+    env = dict(os.environ, IRIS_POST_IN_KERNEL='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(np.load(out), ref)

@@ -232,6 +232,14 @@ def test_default_mel_matrix_is_the_tf_restatement():
     from challenge_b200.engine import default_mel_matrix
     from oracle.transforms import linear_to_mel_weight_matrix
     assert np.array_equal(default_mel_matrix(80), linear_to_mel_weight_matrix(80, 257, 16000))
+    # the product's matrix against the independent float64 golden (not only against the oracle's copy
+    # of the same restatement): tests/golden/mel_matrix_80.json, scripts/make_mel_golden.py
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'mel_matrix_80.json')))
+    w = default_mel_matrix(80)
+    assert (w != 0).sum() == g['nnz'] and (w != 0).sum(0).tolist() == g['taps_per_column']
+    assert np.abs(w.sum(0) - np.array(g['column_sums'])).max() < 4e-5
+    assert max(abs(float(w[f, j]) - v) for f, j, v in g["entries"]) < 2e-5
     assert np.array_equal(default_mel_matrix(40, lower_edge_hertz=80.0, upper_edge_hertz=7600.0),
                           linear_to_mel_weight_matrix(40, 257, 16000, 80.0, 7600.0))
 

@@ -159,20 +159,35 @@ def test_stft_against_float64_restatement():
 
 
 def test_mel_matrix_structure():
-    """PARITY UNPINNED (transforms_test.py:45-55 is shape-only): TF-2.2 semantics restated in
-    fp32; structure and a float64 rebuild agree."""
+    """PARITY UNPINNED by the reference (transforms_test.py:45-55 is shape-only).  The TF-2.2
+    semantics restated in fp32 (oracle) are pinned to tests/golden/mel_matrix_80.json, built by
+    scripts/make_mel_golden.py from the published formula in float64, independently of oracle/
+    and of the product: support (231 non-zeros, rows 5..121, taps per filter), every column and
+    row sum, every entry of 12 columns."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'mel_matrix_80.json')))
     w = T.linear_to_mel_weight_matrix(80, 257, 16000)
-    assert w.shape == (257, 80) and w.dtype == np.float32
-    assert (w != 0).sum() == 231 and not w[0].any()
+    assert w.shape == tuple(g['shape']) and w.dtype == np.float32
+    assert (w != 0).sum() == g['nnz'] == 231 and not w[0].any()
     rows = np.nonzero(w.sum(1))[0]
-    assert rows[0] == 5 and rows[-1] == 121 and (w != 0).sum(1).max() == 2
+    assert rows[0] == g['first_row'] == 5 and rows[-1] == g['last_row'] == 121
+    assert (w != 0).sum(1).max() == g['max_taps_per_row'] == 2
+    assert (w != 0).sum(0).tolist() == g['taps_per_column']
+    # fp32 build (mel values ~2000 carry 1.2e-4 of rounding, a triangle is ~24 mel wide) vs float64
+    assert np.abs(w.sum(0) - np.array(g['column_sums'])).max() < 4e-5
+    assert np.abs(w.sum(1) - np.array(g['row_sums'])).max() < 1e-5
+    assert len(g['entries']) >= 30
+    for f, j, v in g['entries']:
+        assert abs(float(w[f, j]) - v) < 2e-5, (f, j)   # measured 1.06e-5 at (40, 40)
+    # and a second float64 rebuild inline
     lin = np.linspace(0, 8000, 257)[1:]
     h2m = lambda f: 1127.0 * np.log1p(np.asarray(f, np.float64) / 700.0)
     e = np.linspace(h2m(125.0), h2m(3800.0), 82)
     sm = h2m(lin)[:, None]
     w64 = np.maximum(0, np.minimum((sm - e[None, :-2]) / (e[None, 1:-1] - e[None, :-2]),
                                    (e[None, 2:] - sm) / (e[None, 2:] - e[None, 1:-1])))
-    assert np.abs(w[1:] - w64).max() < 5e-4
+    assert np.abs(w[1:] - w64).max() < 2e-5
 
 
 def test_label_downsample_semantics():
