@@ -380,8 +380,10 @@ typedef struct iris_step_io {
     float* d_labels_vtk;      /* DEVICE [B,V,T,K] or NULL (make_pipeline's label output) */
     uint8_t* d_keep;          /* DEVICE [B,V] or NULL */
     /* optional metric leg on this step's frame labels (metrics.py:217-298), enqueued on the
-     * context's own side stream right behind the labels kernel so that it runs beside the
-     * feature kernel: */
+     * context's own side stream.  For IRIS_FEAT_LOGMEL_MINMAX it forks behind the feature kernel and
+     * runs beside the second pass (the labels and the feature kernel stay adjacent in `stream`, and the
+     * persistent feature grid finds every SM free); for the other modes it forks right behind the
+     * labels kernel and runs beside the feature kernel: */
     const float* d_y_pred;    /* DEVICE [B,T,K] model output, or NULL: no metric leg */
     float threshold;          /* 0.5 */
     int32_t* d_triples;       /* DEVICE [B,3] (n_true, n_pred, correct) of the local clips; with a
@@ -396,7 +398,9 @@ typedef struct iris_step_io {
 } iris_step_io;
 
 /* One batch.  Everything is enqueued on `stream` (the metric leg on the context's side stream,
- * ordered behind the labels kernel); returns when the launches are queued.  The host blocks only
+ * ordered behind the labels kernel); returns when the launches are queued.  The labels kernel also
+ * builds the per-tile stage lists of the feature kernel (the keep flags it decides are their only
+ * input that is not in the plan), so a step is plan upload -> k_labels -> k_fused (-> k_logmel_post).  The host blocks only
  * when it is more than four batches ahead of the device (ring of pinned plan buffers). */
 int iris_step(iris_ctx* ctx, const iris_step_config* cfg, const iris_step_io* io, iris_stream stream);
 /* Make `stream` wait for the metric leg (counts and their all-reduce) issued `lag` iris_step
