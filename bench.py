@@ -409,14 +409,22 @@ def run_gpu_arm(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        _, _, keep = eng.labels()   # keep flags of the last plan -> algorithmic bytes (kept sources only)
-        keep = keep.cpu().numpy()
-        bi, bo = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep)
-        # the launch the roofline hook timed: the whole batch, or the first part of a split batch
-        k_clips = eng.profile_clips() or st['b']
-        ki, ko = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep, clips=(0, k_clips))
+        # algorithmic bytes (kept sources only) of EVERY timed step: the steps are replayed
+        # untimed with the same uniforms, the keep flags of each plan read back (they differ by ~2 % from
+        # draw to draw, which a figure taken from the last plan alone would carry into `frac`)
+        k_clips = eng.profile_clips() or st['b']   # the launch the roofline hook timed: the batch, or the first part of a split batch
+        alg = ker = 0
+        for s in range(n_steps):
+            one_step(st, us[n_warm + s], s)
+            eng.counts_wait(0)
+            _, _, keep = eng.labels()
+            keep = keep.cpu().numpy()
+            bi, bo = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep)
+            ki, ko = eng.plan_bytes(L.FEAT_LOGMEL_MINMAX, keep, clips=(0, k_clips))
+            alg += bi + bo
+            ker += ki + ko
         return dict(total_ms=total_ms, total_ms_max=float(t.item()), fused_ms=fused_ms, n_fused=n_fused,
-                    alg_bytes=bi + bo, kernel_bytes=ki + ko, kernel_clips=k_clips)
+                    alg_bytes=alg / n_steps, kernel_bytes=ker / n_steps, kernel_clips=k_clips)
 
     # ---- device-timed: inputs (banks) resident, the uniforms of every step drawn beforehand ----
     st = step_setup(B, Bg, lo)
@@ -518,6 +526,12 @@ def run_gpu_arm(args):
         del st3
         torch.cuda.empty_cache()
 
+    # ---- N = 1: BASELINE configs[4], the input-bound check.  sj_train.py's Keras step cannot run
+    # (TensorFlow is absent), so a SUBSTITUTE consumer of the pipeline's tensors is timed beside it ----
+    consumer = None
+    if world == 1 and not args.no_consumer_check:
+        consumer = consumer_check(dev, B, T, K, r['total_ms'] / args.steps)
+
     peak, peak_src = measured_peak()
     fused_avg_ms = r['fused_ms'] / max(r['n_fused'], 1)
     achieved = r['kernel_bytes'] / (fused_avg_ms / 1e3) / 1e9 if fused_avg_ms > 0 else 0.0
@@ -568,6 +582,8 @@ def run_gpu_arm(args):
                                        'copied to the host; labels + counts still read back'}
     if cfg3 is not None:
         out['configs3_one_gpu'] = cfg3
+    if consumer is not None:
+        out['input_bound_check'] = consumer
     if world > 1:
         out['config']['host_binding'] = ('each rank pinned to the %d cores NVML lists for its GPU' % len(numa_cores)
                                          if numa_cores else 'none (NVML affinity not available)')
@@ -589,6 +605,63 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def consumer_check(dev, B, T, K, pipeline_ms):
+    """BASELINE configs[4] ("pipeline feeding a train step: is the model input-bound?").  The
+    reference's consumer is a Keras EfficientNet step (sj_train.py:158-188, 454-513) and cannot run
+    here; the stand-in is a small bf16 conv net over the pipeline's own tensors ([B,80,T,2] features,
+    [B,T,3] frame labels): 4 stride-2 conv stages + a frame-wise head, forward + backward + SGD in
+    torch (library kernels; NOT part of the measured path, reported beside it)."""
+    import torch
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            ch = [CFG['n_chan'], 32, 64, 128, 256]
+            self.convs = torch.nn.ModuleList([torch.nn.Conv2d(ch[i], ch[i + 1], 3, stride=(2, 1), padding=1)
+                                              for i in range(4)])
+            self.head = torch.nn.Conv1d(256 * (CFG['n_mels'] // 16), K, 1)
+
+        def forward(self, x):                      # [B, mel, T, C]
+            x = x.permute(0, 3, 1, 2)
+            for c in self.convs:
+                x = torch.relu(c(x))
+            return self.head(x.flatten(1, 2)).transpose(1, 2)
+
+    try:
+        net = Net().to(dev).to(memory_format=torch.channels_last)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+        x = torch.randn(B, CFG['n_mels'], T, CFG['n_chan'], device=dev)
+        y = (torch.rand(B, T, K, device=dev) < 0.3).float()
+
+        def train_step():
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(net(x).float(), y)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+
+        for _ in range(3):
+            train_step()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            train_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        del net, opt, x, y
+        torch.cuda.empty_cache()
+    except Exception as ex:   # the check is a side report: never fail the bench line over it
+        return {'workload': 'BASELINE configs[4] input-bound check', 'unavailable': repr(ex)[:200]}
+    return {'workload': 'BASELINE configs[4] input-bound check with a SUBSTITUTE consumer (TensorFlow / sj_train.py '
+                        'cannot run here): 4-stage bf16 conv net + frame-wise head on [B,80,626,2] -> [B,626,3], '
+                        'forward + backward + SGD in torch, batch %d' % B,
+            'consumer_ms_per_step': ms, 'pipeline_ms_per_step': pipeline_ms,
+            'pipeline_share_of_consumer_step': pipeline_ms / ms,
+            'input_bound': bool(pipeline_ms > ms)}
 
 
 def cpu_baseline():
@@ -624,6 +697,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
     ap.add_argument('--batch', type=int, default=0, help='N = 1 only: another batch size (experiments)')
     ap.add_argument('--no-cfg3', action='store_true', help='skip the 8192-clip single-GPU leg (profiling runs)')
+    ap.add_argument('--no-consumer-check', action='store_true', help='skip the configs[4] substitute-consumer leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

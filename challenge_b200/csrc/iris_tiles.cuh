@@ -8,7 +8,10 @@
 
 namespace iris {
 
-constexpr int kMaxStages = 24;   // mixing segments of one clip (upper bound on stages per tile; the ring copy takes <= 30)
+#ifndef IRIS_MAX_STAGES
+#define IRIS_MAX_STAGES 24
+#endif
+constexpr int kMaxStages = IRIS_MAX_STAGES;   // mixing segments of one clip (upper bound on stages per tile; the ring copy takes <= 30)
 
 struct StageDesc {
     const float* src;      // first row of the stage in the pair plane of the source

@@ -1055,11 +1055,12 @@ static void fused_schedule(FusedParams& p, long long n_tiles, int grid) {
         const char* e1 = getenv("IRIS_TAIL1");
         const char* e2 = getenv("IRIS_TAIL2");
         t_one = e1 ? atoi(e1) : 2;
-        t_mid = e2 ? atoi(e2) : 4;
+        t_mid = e2 ? atoi(e2) : 6;
     }
     const int unit = p.pair_merge ? 2 : 1;   // both channel pairs of a (clip, time) range in one claim
     p.chunk_tail = unit;
-    p.chunk_mid = p.chunk / 2 > unit ? p.chunk / 2 : unit;
+    p.chunk_mid = (p.chunk / 2) / unit * unit;
+    if (p.chunk_mid < unit) p.chunk_mid = unit;
     if (p.chunk <= unit) {   // nothing to shrink
         p.chunk_mid = p.chunk_tail = p.chunk;
         p.n_big = 0x7fffffff;

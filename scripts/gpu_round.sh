@@ -17,12 +17,12 @@ refbench)
   cat gpurun_out/bench_ref.json ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e \
+     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-cfg3 --no-consumer-check \
      > gpurun_out/launches_bench.log 2>&1
   tail -2 gpurun_out/launches_bench.log ;;
 ncu)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 4 -c 2 \
-     -f -o gpurun_out/prof_fused python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e \
+     -f -o gpurun_out/prof_fused python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-cfg3 --no-consumer-check \
      > gpurun_out/ncu_bench.log 2>&1
   tail -2 gpurun_out/ncu_bench.log ;;
 kbench)

@@ -319,3 +319,41 @@ np.save(%r, b)
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert np.array_equal(np.load(out), ref)
+
+
+def test_tile_lists_built_by_k_labels_match_k_tiles(engine, workload_factory, monkeypatch):
+    """k_labels builds the per-tile stage lists of the feature launch it is told about (the mode of
+    the previous feature launch, or iris_step's mode); a feature launch with another layout -- another
+    mode family, only_voice / only_noise, another plan -- must notice and run k_tiles.  Every order
+    of calls gives the bits of the plain labels -> k_tiles -> k_fused path."""
+    from challenge_b200 import _lib as L
+    from challenge_b200.plan import draw_batch
+    engine.set_mel(80)
+    w = workload_factory(2)
+    plans = [draw_batch(np.random.default_rng(s), 5, 300, w.bg_frames, w.voice_frames, w.noise_frames, max_voices=5,
+                        max_noises=2, snr=-20, min_ratio=2 / 3, n_time_masks=6, n_freq_masks=1) for s in (1, 2)]
+    modes = [L.FEAT_LOGMEL_MINMAX, L.FEAT_COMPLEX, L.FEAT_MEL, L.FEAT_MAGPHASE, L.FEAT_LOGMEL]
+    monkeypatch.setenv('IRIS_NO_LABEL_TILES', '1')
+    ref = {}
+    for i, d in enumerate(plans):
+        engine.upload_plan(d)
+        engine.labels()
+        for m in modes:
+            ref[i, m] = engine.features(m).clone()
+        ref[i, 'voice'] = engine.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES).clone()
+    monkeypatch.delenv('IRIS_NO_LABEL_TILES')
+    order = [(0, modes[0]), (0, modes[1]), (1, modes[1]), (1, modes[0]), (0, modes[3]), (0, modes[2]), (1, modes[4]),
+             (1, modes[4]), (0, modes[0]), (0, modes[0])]
+    for i, m in order:
+        engine.upload_plan(plans[i])
+        engine.labels()                       # hinted with the mode of the previous feature launch
+        got = engine.features(m)
+        assert torch_equal(got, ref[i, m]), (i, m)
+        # another segment selection between two launches of one mode
+        assert torch_equal(engine.features(L.FEAT_COMPLEX, select=L.SELECT_VOICES), ref[i, 'voice'])
+        assert torch_equal(engine.features(m), ref[i, m]), (i, m, 'second launch on cached tile lists')
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
