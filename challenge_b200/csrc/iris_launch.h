@@ -78,6 +78,9 @@ cudaError_t launch_avg_pool_time(const float* y, float* out, int B, int T, int K
 cudaError_t launch_cos_sim(const float* y_true, const float* y_pred, float* out, int B, int T, int K,
                            cudaStream_t st);
 
+// data_utils.normalize (data_utils.py:32-34); acc: one double of scratch
+cudaError_t launch_normalize(const float* x, float* out, size_t n, double* acc, cudaStream_t st);
+
 cudaError_t launch_phase_vocoder(const float* x, float* out, int F, int T, int C, int T_out, const int32_t* i0,
                                  const int32_t* i1, const float* alpha, float adv_step, cudaStream_t st);
 cudaError_t launch_sum_pool2(const float* y, float* out, int B, int T, int K, float scale, cudaStream_t st);

@@ -99,6 +99,15 @@ int iris_op_pointwise(iris_ctx* c, int op, const float* x, float* out, int64_t r
     return IRIS_OK;
 }
 
+int iris_op_normalize(iris_ctx* c, const float* x, float* out, int64_t n, iris_stream stream) {
+    int rc = begin(c);
+    if (rc) return rc;
+    if (!x || !out || n < 1) return fail(IRIS_ERR_INVALID, "iris_op_normalize: bad argument");
+    CU(c->op_small.reserve(256));
+    CU(launch_normalize(x, out, size_t(n), c->op_small.as<double>(), static_cast<cudaStream_t>(stream)));
+    return IRIS_OK;
+}
+
 int iris_op_chan_map(iris_ctx* c, int kind, const float* x, float* out, int64_t rows, int w_in,
                      int w_out, const float* factor, int64_t n_samples, int64_t rows_per_sample,
                      iris_stream stream) {

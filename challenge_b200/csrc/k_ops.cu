@@ -453,4 +453,39 @@ cudaError_t launch_density_labels(const float* y, float* out, size_t outer, int 
     return cudaGetLastError();
 }
 
+// ---- data_utils.normalize (data_utils.py:32-34): x / (10 * sqrt(mean(x^2))) over the whole clip ----
+// Same arithmetic as the bank registration (k_bank.cu): squares summed in fp64, mean and
+// sqrt(.) * 10 in fp32 like torch, then a division per sample.
+__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ x, size_t n, double* __restrict__ acc) {
+    double a = 0.0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        a += double(v) * double(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        atomicAdd(acc, t);
+    }
+}
+__global__ void __launch_bounds__(256) k_rms_scale(const float* __restrict__ x, float* __restrict__ out, size_t n,
+                                                   double* __restrict__ acc) {
+    const float rms = sqrtf(float(*acc / double(n))) * 10.f;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        out[i] = x[i] / rms;
+}
+cudaError_t launch_normalize(const float* x, float* out, size_t n, double* acc, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = unsigned(n / 1024 < 1 ? 1 : (n / 1024 > 592 ? 592 : n / 1024));
+    k_sumsq<<<grid, 256, 0, st>>>(x, n, acc);
+    k_rms_scale<<<grid, 256, 0, st>>>(x, out, n, acc);
+    return cudaGetLastError();
+}
+
 }  // namespace iris

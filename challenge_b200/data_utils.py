@@ -39,12 +39,12 @@ def load_wav(wav_fname):
 
 
 def normalize(wav):
-    """data_utils.py:32-34 -- a scalar RMS of the whole clip; folded into the STFT kernel's
-    bank preparation on the fused path, kept here as plain tensor math for API parity."""
-    import torch
-    wav = torch.as_tensor(wav)
-    rms = torch.sqrt(torch.mean(torch.pow(wav, 2))) * 10
-    return wav / rms
+    """data_utils.py:32-34 -- a scalar RMS of the whole clip (``iris_op_normalize``: the arithmetic
+    of the bank registration, which applies it on the fused path)."""
+    t = O.dev(wav)
+    out = O.empty(t.shape)
+    O.call('iris_op_normalize', O.ptr(t), O.ptr(out), t.numel())
+    return out
 
 
 def minmax(x, y=None):

@@ -213,6 +213,10 @@ enum {
     IRIS_PW_LOG_ON_MEL = 3,          /* data_utils.py:50-55; any shape, pass width = 1        */
     IRIS_PW_MULTIPLY = 4             /* data_utils.py:120-123; `param_f` = multiply_factor    */
 };
+/* data_utils.normalize (data_utils.py:32-34): d_out = d_x / (10 * sqrt(mean(d_x^2))) over all n
+ * elements (every channel and sample of one clip); squares summed in fp64, the rest in fp32 as in
+ * the bank registration.  In place is allowed. */
+int iris_op_normalize(iris_ctx* ctx, const float* d_x, float* d_out, int64_t n, iris_stream stream);
 int iris_op_pointwise(iris_ctx* ctx, int op, const float* d_x, float* d_out, int64_t rows,
                       int width, int param_i, float param_f, iris_stream stream);
 /* Channel remaps on [rows, w_in] -> [rows, w_out] (out must NOT alias x):

@@ -134,6 +134,22 @@ def test_load_wav_and_feature_chain(mods):
     assert nmax_err(_np(x), r) < 1e-4
 
 
+def test_normalize_runs_on_the_device(mods):
+    """data_utils.normalize (data_utils.py:32-34) as iris_op_normalize: the RMS of the whole clip
+    (all channels), squares summed in fp64 -- against the oracle's torch fp32 form and a float64 value."""
+    from oracle import data_utils as OD
+    _, _, D, _ = mods
+    rng = np.random.default_rng(11)
+    for shape in [(2, 160000), (4, 40001), (1, 300), (3, 7)]:
+        wav = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+        got = _np(D.normalize(wav))
+        assert got.shape == wav.shape
+        assert nmax_err(got, OD.normalize(wav)) < 2e-6
+        ref64 = wav.astype(np.float64) / (10 * np.sqrt(np.mean(wav.astype(np.float64) ** 2)))
+        assert nmax_err(got, ref64) < 5e-7
+        assert abs(float(np.sqrt(np.mean(got.astype(np.float64) ** 2))) - 0.1) < 1e-7
+
+
 def test_minmax_log_labels_and_remaps(mods):
     from oracle import data_utils as OD
     _, _, D, _ = mods
