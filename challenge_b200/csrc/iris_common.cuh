@@ -271,6 +271,33 @@ __device__ __forceinline__ void fast_atan2f_x2(float y0, float x0, float y1, flo
     r0 = copysignf(q0, y0);
     r1 = copysignf(q1, y1);
 }
+// Two atan2 for cells whose magnitude m = sqrt(x^2 + y^2) is already there (the mag/phase epilogue of
+// k_fused): half-angle form.  With d = m + |x|, t = y / d lies in [-1, 1] for every (x, y), so the
+// octant reduction (two abs, max, min, compare, two fix-ups per value) disappears:
+//     atan2(y, x) = 2 atan(t)                      x >= +0
+//                 = copysign(pi, y) - 2 atan(t)    x <= -0
+// Same degree-17 polynomial (coefficients doubled: exact), |error| <= ~7e-7 rad.  Signed zeros as
+// IEEE atan2: y = +-0 gives t = +-0, hence +-0 or +-pi by the sign bit of x; x = y = 0 has d clamped
+// to a tiny positive number so that t stays +-0.  23 instructions for two values instead of 32.
+__device__ __forceinline__ void fast_atan2f_mag_x2(float y0, float x0, float m0, float y1, float x1, float m1,
+                                                   float& r0, float& r1) {
+    // (|y| in the max keeps |t| <= 1 when m underflowed to 0 for denormal-range inputs; one FMNMX3)
+    const float d0 = fmaxf(fmaxf(m0 + fabsf(x0), fabsf(y0)), 1e-30f), d1 = fmaxf(fmaxf(m1 + fabsf(x1), fabsf(y1)), 1e-30f);
+    const cpx t{__fdividef(y0, d0), __fdividef(y1, d1)};
+    const cpx s = cmul2(t, t);
+    cpx r{2.f * 0.0028662257f, 2.f * 0.0028662257f};
+    r = cfma2(r, s, cpx{2.f * -0.0161657367f, 2.f * -0.0161657367f});
+    r = cfma2(r, s, cpx{2.f * 0.0429096138f, 2.f * 0.0429096138f});
+    r = cfma2(r, s, cpx{2.f * -0.0752896400f, 2.f * -0.0752896400f});
+    r = cfma2(r, s, cpx{2.f * 0.1065626393f, 2.f * 0.1065626393f});
+    r = cfma2(r, s, cpx{2.f * -0.1420889944f, 2.f * -0.1420889944f});
+    r = cfma2(r, s, cpx{2.f * 0.1999355085f, 2.f * 0.1999355085f});
+    r = cfma2(r, s, cpx{2.f * -0.3333314528f, 2.f * -0.3333314528f});
+    r = cfma2(r, s, cpx{2.f, 2.f});
+    r = cmul2(r, t);
+    r0 = (__float_as_uint(x0) >> 31) ? copysignf(3.14159265358979324f, y0) - r.x : r.x;
+    r1 = (__float_as_uint(x1) >> 31) ? copysignf(3.14159265358979324f, y1) - r.y : r.y;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

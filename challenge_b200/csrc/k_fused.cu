@@ -156,7 +156,11 @@ __device__ __forceinline__ float4 make_piece(const FusedParams& p, int f, float 
     if (MODE != FM_COMPLEX) {
         a0 = sqrt_approx(fmaf(r0, r0, i0 * i0));   // transforms.py:116
         a1 = sqrt_approx(fmaf(r1, r1, i1 * i1));
+#ifdef IRIS_ATAN2_OCTANT
         fast_atan2f_x2(i0, r0, i1, r1, b0, b1);    // transforms.py:117
+#else
+        fast_atan2f_mag_x2(i0, r0, a0, i1, r1, a1, b0, b1);    // transforms.py:117, from the magnitudes above
+#endif
         if (MODE == FM_LOGMAGPHASE) {            // transforms.py:80-86
             a0 = __logf(a0 + 1e-8f);   // MUFU.LG2 * ln 2, as in the log-mel epilogue (|error| ~1e-6)
             a1 = __logf(a1 + 1e-8f);
