@@ -14,21 +14,26 @@
 //
 // Structure.  A tile is FR consecutive output frames of one (clip, channel pair); a CTA has
 // FR consumer warps (warp j owns frame j of the tile) and one producer warp.
-//  * k_tiles (one thread per tile) compacts, for every tile, the mixing segments that are
-//    kept and overlap it into a TileBlock (stage descriptors + the tile's mask bits).
-//  * Tiles are claimed in chunks of consecutive tiles from a global counter.  The producer warp
-//    copies the TileBlock of each tile into a shared-memory descriptor ring and fetches every
-//    stage -- (j_cnt + 1) contiguous 2 KB rows of the pair-interleaved bank -- with ONE
-//    cp.async.bulk (TMA 1-D) into a ring of 3 (mel) or 2 (spectrogram modes) stage buffers: full[slot] completes when
-//    the bytes have landed, empty[slot] when all FR consumer warps have read the slot.
+//  * For every tile a TileBlock lists the mixing segments that are kept and overlap it (stage
+//    descriptors + the tile's mask bits; iris_tiles.cuh).  The blocks are written by the label
+//    kernel (k_labels, which decides the keep flags) or, without a label pass in front, by k_tiles.
+//  * Tiles are claimed in chunks of consecutive tiles that shrink towards the end of the launch
+//    (fused_schedule): the first claim of a CTA is its block index, the later ones come from a global
+//    counter.  The producer warp copies the TileBlock of each tile into a shared-memory descriptor
+//    ring and fetches every stage -- (j_cnt + 1) contiguous 2 KB rows of the pair-interleaved bank --
+//    with ONE cp.async.bulk (TMA 1-D) into a ring of 3 (mel) or 2 (spectrogram modes) stage buffers:
+//    full[slot] completes when the bytes have landed, empty[slot] when all FR consumer warps have
+//    read the slot.
 //  * Consumer warps never synchronise with each other: each waits on full[slot], accumulates
 //    gain * frame into its 16 complex registers per lane, releases the slot, and after the
 //    last stage runs the warp FFT (fftwarp.cuh: 16-point FFT in registers, twiddle, one
 //    exchange through its private 4.25 KB of shared memory, radix-2 DIF + 16-point FFT) and
 //    the epilogue.  Rows shared by adjacent frames are read from the same slot, so every
 //    source row enters the SM once per tile.
-//  * LOGMEL_MINMAX: per-warp min/max go to global atomics; k_logmel_post (k_post.cu)
-//    normalises and logs the batch in place right after, while it is still in L2.
+//  * LOGMEL_MINMAX: the warps of a CTA combine the extrema of a run of tiles of one clip in shared
+//    memory and the last one sends them to global atomics; k_logmel_post (k_post.cu) normalises and
+//    logs the batch in place right after, while it is still in L2 (EPI_POST: a post warp per CTA
+//    does that inside this kernel instead -- opt-in, measured equal at the step level).
 #include <cstdio>
 #include <cstdlib>
 

@@ -409,3 +409,56 @@ def test_full_size_cfg4_shards_equal_the_whole_batch(engine, workload_factory):
     xn = x[::1024].cpu().numpy()                       # every clip spans [log 1e-8, log(1 + 1e-8)]
     assert np.allclose(xn.reshape(len(xn), -1).min(1), np.log(np.float32(1e-8)), rtol=0, atol=1e-5)
     assert np.allclose(xn.reshape(len(xn), -1).max(1), 0, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', range(10))
+def test_random_small_shapes_against_the_oracle(case):
+    """Randomised shapes around the edges of the tile / claim machinery: 1..4 channels, n_frame from
+    a handful to a few hundred (ragged last tile, fewer tiles than CTAs, fewer tiles than one claim),
+    batch 1..9, with / without voices, noises and masks, every feature mode.  Labels, keep flags and
+    masks bit-exact, features within the bars above."""
+    from challenge_b200 import _lib as L
+    from challenge_b200.engine import Engine
+    from challenge_b200.plan import draw_batch
+    from challenge_b200.synth import synthetic_banks
+    from oracle import chain
+    rng = np.random.default_rng(9000 + case)
+    C = int(rng.integers(1, 5))
+    T = int(rng.choice([3, 8, 9, 17, 40, 63, 64, 65, 130, 301]))
+    B = int(rng.integers(1, 10))
+    V = int(rng.integers(0, 5))
+    M = int(rng.integers(0, 4)) if V > 0 else 0
+    masks = bool(rng.integers(0, 2))
+    bgs, voices, labels, noises = synthetic_banks(500 + case, C, n_bg=3, n_voice=7, n_noise=3,
+                                                  bg_seconds=float(rng.choice([1.0, 2.5, 6.0])), lo_s=0.2, hi_s=1.5)
+    eng = Engine(0)
+    try:
+        eng.set_mel(80)
+        bf = eng.register_bank(L.BANK_BG, bgs)
+        vf = eng.register_bank(L.BANK_VOICE, voices, labels=labels)
+        nf = eng.register_bank(L.BANK_NOISE, noises)
+        try:
+            d = draw_batch(rng, B, T, bf, vf if V else None, nf if M else None, max_voices=V, max_noises=M, snr=-20,
+                           min_ratio=2 / 3, n_time_masks=6 if masks and T > 24 else 0, n_freq_masks=1 if masks else 0)
+        except ValueError:      # an empty offset range for this (voice length, n_frame): the reference raises too
+            pytest.skip('draw raises like the reference')
+        eng.upload_plan(d)
+        ob, ov, on = chain.OracleBank(bgs), chain.OracleBank(voices), chain.OracleBank(noises)
+        if V:
+            frame, _, keep = eng.labels()
+        for mode, name in ((L.FEAT_LOGMEL_MINMAX, 'logmel_minmax'), (L.FEAT_COMPLEX, 'complex'),
+                           (L.FEAT_MAGPHASE, 'magphase'), (L.FEAT_MEL, 'mel')):
+            got = eng.features(mode).cpu().numpy()
+            ref, ref_y, _, ref_keep = chain.dataset_batch(ob, ov if V else None, labels if V else None,
+                                                          on if M else None, d, mode=name)
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            if name == 'magphase':
+                assert nmax_err(got[..., :C], ref[..., :C]) < TOL, name
+                assert phase_report(ref[..., :C], got[..., C:], ref[..., C:])['gate1e-3'] < PHASE_TOL
+            else:
+                assert nmax_err(got, ref) < TOL, (name, C, T, B, V, M)
+        if V:
+            assert np.array_equal(frame.cpu().numpy(), ref_y)
+            assert np.array_equal(keep.cpu().numpy(), np.stack(ref_keep))
+    finally:
+        eng.close()
