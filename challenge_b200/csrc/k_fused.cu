@@ -85,9 +85,11 @@ constexpr int OFF_MSTART = OFF_TW1 + 2 * 32 * 16;            // uint32 [kMaxMel]
 constexpr int OFF_MW = OFF_MSTART + kMaxMel * 4;             // float [mel_taps][32]
 static_assert(OFF_TW1 % 16 == 0 && OFF_MW % 16 == 0, "table alignment");
 
-__host__ __device__ inline uint32_t off_xch(int mel_taps) {
+// float [256]: first half of the periodic Hann window (w[n + 256] = 1 - w[n])
+__host__ __device__ inline uint32_t off_hann(int mel_taps) {
     return (uint32_t(OFF_MW) + uint32_t(mel_taps) * 128u + 127u) & ~127u;
 }
+__host__ __device__ inline uint32_t off_xch(int mel_taps) { return off_hann(mel_taps) + 1024u; }
 __host__ __device__ inline uint32_t off_slots(int mel_taps, int fr) {
     return off_xch(mel_taps) + uint32_t(fr) * uint32_t(kXwBytes);   // kXwBytes % 128 == 0
 }
@@ -562,6 +564,8 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                 float* s_mw = reinterpret_cast<float*>(sm + OFF_MW);
                 for (int i = tid; i < mel_taps * 32; i += FR * 32) s_mw[i] = p.mel_w[i];
             }
+            float* s_hann = reinterpret_cast<float*>(sm + off_hann(mel_taps));
+            for (int i = tid; i < 256; i += FR * 32) s_hann[i] = p.hann[i];
             named_bar_sync(2, FR * 32);   // consumer warps only
         }
         const int j = warp;                        // tile-relative frame of this warp
@@ -569,9 +573,10 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         const float sgn = par ? -1.f : 1.f;
         const int partner = warp_partner(lane);
         const bool l0 = (lane == 0);
-        float w8[8];                               // Hann[n], n = lane + 32 i; Hann[n + 256] = 1 - Hann[n]
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w8[i] = p.hann[lane + 32 * i];
+        // Hann[n], n = lane + 32 q, read from shared memory every frame (8 conflict-free LDS.32): held in
+        // 8 registers per lane it pushed the spectrogram instances into spills -- 2-ch COMPLEX 302 ->
+        // 287 us, 4-ch mel 377 -> 363 us with the table in shared memory, the 2-ch mel instances unchanged
+        const float* w8 = reinterpret_cast<const float*>(sm + off_hann(mel_taps)) + lane;
         unsigned char* xch = sm + off_xch(mel_taps) + warp * kXwBytes;
         const float4* s_tw1 = reinterpret_cast<const float4*>(sm + OFF_TW1) + lane;
         const unsigned char* my_rows = slots + j * 2048 + lane * 8;
@@ -763,8 +768,9 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             if (do_fft) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    v[q] = cscale(v[q], w8[q]);
-                    v[q + 8] = caxpy(-w8[q], v[q + 8], v[q + 8]);
+                    const float wq = w8[32 * q];
+                    v[q] = cscale(v[q], wq);
+                    v[q + 8] = caxpy(-wq, v[q + 8], v[q + 8]);
                 }
                 {
                     const float4 wa = s_tw1[0], wb = s_tw1[32];
