@@ -105,6 +105,7 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p]),
     'iris_op_random_shift': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    'iris_debug_claims': (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'iris_op_normalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'iris_op_pointwise': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                     C.c_int, C.c_float, C.c_void_p]),

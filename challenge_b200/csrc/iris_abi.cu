@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "iris_ctx.h"
+#include "iris_tiles.cuh"
 
 using namespace iris;
 
@@ -1190,6 +1191,17 @@ int iris_er_counts_pooled(iris_ctx* c, const float* y_true, int T, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(launch_metric_counts(y_true, y_pred, B, T, T_pred, K, thr, d_triples, nullptr, nullptr, st));
     if (d_er) CU(launch_er_finalize(d_triples, B, d_er, st));
+    return IRIS_OK;
+}
+
+int iris_debug_claims(int64_t n_tiles, int grid, int chunk, int pair_merge, int64_t q, int32_t* schedule5,
+                      int64_t* first, int32_t* len) {
+    if (n_tiles < 0 || grid < 1 || chunk < 1 || !schedule5 || !first || !len)
+        return fail(IRIS_ERR_INVALID, "iris_debug_claims: bad argument");
+    fused_debug_schedule(n_tiles, grid, chunk, pair_merge, schedule5);
+    int l = 0;
+    *first = claim_range(schedule5[0], schedule5[1], schedule5[2], schedule5[3], schedule5[4], q, l);
+    *len = l;
     return IRIS_OK;
 }
 

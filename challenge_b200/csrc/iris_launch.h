@@ -13,6 +13,7 @@ enum { FUSED_LAUNCH_TILES = 1, FUSED_LAUNCH_KERNEL = 2, FUSED_LAUNCH_PDL = 4 };
 cudaError_t launch_fused(const FusedParams& p, int mode, int num_sms, cudaStream_t stream,
                          int what = FUSED_LAUNCH_TILES | FUSED_LAUNCH_KERNEL);
 size_t fused_smem_bytes(const FusedParams& p, int mode);
+void fused_debug_schedule(long long n_tiles, int grid, int chunk, int pair_merge, int32_t out[5]);
 bool fused_can_post_in_kernel(const FusedParams& p);   // min-max log-mel: second pass inside k_fused (no k_logmel_post)
 int fused_max_segments();      // mixing segments one clip may have
 bool fused_stages_output(int mode, int remap, int fr);   // FusedParams::stage_out for a launch

@@ -32,6 +32,19 @@ static_assert(sizeof(TileBlock) == 32 + 16 * kMaxStages, "TileBlock layout");
 constexpr int kTileBlockBytes = int(sizeof(TileBlock));
 
 
+// Work claims of the persistent feature kernel (k_fused.cu, fused_schedule): claim q covers `chunk`
+// consecutive tiles for q < n_big, `chunk_mid` tiles for the next n_mid claims, `chunk_tail` tiles after
+// that; returns the first tile (>= the tile count: no work left) and the length in `len`.  Shared by the
+// producer warp and the host-side check of the schedule (iris_debug_claims).
+__host__ __device__ inline long long claim_range(int chunk, int chunk_mid, int chunk_tail, long long n_big,
+                                                 long long n_mid, long long q, int& len) {
+    if (q < n_big) { len = chunk; return q * chunk; }
+    q -= n_big;
+    if (q < n_mid) { len = chunk_mid; return n_big * chunk + q * chunk_mid; }
+    len = chunk_tail;
+    return n_big * chunk + n_mid * chunk_mid + (q - n_mid) * chunk_tail;
+}
+
 // tile = (clip * tiles_per_clip + time_tile) * n_pairs + pair, per_clip = tiles_per_clip * n_pairs
 __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile, int per_clip) {
     const int FR = p.fr;

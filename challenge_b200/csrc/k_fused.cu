@@ -36,6 +36,7 @@
 //    does that inside this kernel instead -- opt-in, measured equal at the step level).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "fftwarp.cuh"
 #include "iris_common.cuh"
@@ -262,11 +263,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     const int CH = p.chunk, CM = p.chunk_mid, CT = p.chunk_tail;
     const long long n_big = p.n_big, n_mid = p.n_mid;
     auto claim_range = [&](long long q, int& len) -> long long {
-        if (q < n_big) { len = CH; return q * CH; }
-        q -= n_big;
-        if (q < n_mid) { len = CM; return n_big * CH + q * CM; }
-        len = CT;
-        return n_big * CH + n_mid * CM + (q - n_mid) * CT;
+        return iris::claim_range(CH, CM, CT, n_big, n_mid, q, len);
     };
     auto load_block = [&](int tile) -> int4 {
         const unsigned char* blk = p.tile_blocks + size_t(tile + p.tile_first) * p.tile_stride;
@@ -1087,6 +1084,17 @@ static void fused_schedule(FusedParams& p, long long n_tiles, int grid) {
     const long long mid = rem < tail_mid ? rem : tail_mid;
     p.n_big = int32_t((rem - mid) / p.chunk);
     p.n_mid = int32_t((rem - (long long)p.n_big * p.chunk) / p.chunk_mid);
+}
+
+// the schedule a launch of n_tiles tiles on `grid` CTAs would get: {chunk, chunk_mid, chunk_tail, n_big, n_mid}
+void fused_debug_schedule(long long n_tiles, int grid, int chunk, int pair_merge, int32_t out[5]) {
+    FusedParams p;
+    memset(&p, 0, sizeof p);
+    p.chunk = chunk;
+    p.pair_merge = pair_merge;
+    if (p.pair_merge && (p.chunk & 1)) ++p.chunk;
+    fused_schedule(p, n_tiles, grid);
+    out[0] = p.chunk; out[1] = p.chunk_mid; out[2] = p.chunk_tail; out[3] = p.n_big; out[4] = p.n_mid;
 }
 
 #ifdef IRIS_TRACE

@@ -175,6 +175,12 @@ int iris_plan_bytes(iris_ctx* ctx, int mode, const uint8_t* host_keep, int64_t* 
 int iris_plan_bytes_clips(iris_ctx* ctx, int mode, const uint8_t* host_keep, int clip_lo, int clip_hi,
                           int64_t* bytes_in, int64_t* bytes_out);
 
+/* Debug / test hook (no device needed): the work-claim schedule a k_fused launch of n_tiles tiles on `grid`
+ * persistent CTAs gets -- schedule5 = {chunk, chunk_mid, chunk_tail, n_big, n_mid} -- and the tile range of
+ * claim q under it (first >= n_tiles: no work left).  tests/test_host_logic.py checks that the claims
+ * cover every tile exactly once. */
+int iris_debug_claims(int64_t n_tiles, int grid, int chunk, int pair_merge, int64_t q, int32_t* schedule5,
+                      int64_t* first, int32_t* len);
 /* Measurement hook for bench.py's roofline: when enabled, every launch of the fused
  * feature kernel inside iris_features() is bracketed by cudaEvents on the launching stream;
  * iris_profile_read() synchronises them and returns the summed device time. */

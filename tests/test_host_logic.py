@@ -328,3 +328,37 @@ def test_default_mel_matrix_has_the_shape_the_fixed_kernel_instances_assume():
     assert [n + (n & 1) for n in rounds] == [2, 4, 6] and hi < 128
     src = open(os.path.join(ROOT, 'challenge_b200', 'csrc', 'k_fused.cu')).read()
     assert 'return r == 0 ? 2 : (r == 1 ? 4 : (r == 2 ? 6 : 0));' in src
+
+
+def test_work_claim_schedule_covers_every_tile_once():
+    """k_fused hands its tiles out in claims that shrink towards the end of a launch (whole chunks, half
+    chunks, single tiles; pairs of tiles for 4-channel clips whose two channel pairs share a store
+    phase).  For any tile count / grid / chunk the claims 0, 1, 2, ... must tile [0, n_tiles) exactly
+    once, in order, and -- with merged pairs -- start on even tiles with even lengths."""
+    from challenge_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    cases = [(20224, 296, 6, 0), (2528, 296, 6, 0), (1, 296, 6, 0), (5, 1, 4, 0), (40448, 296, 6, 1),
+             (2, 296, 6, 1), (647168, 296, 6, 0), (79, 296, 1, 0), (158, 64, 2, 1)]
+    cases += [(int(rng.integers(1, 5000)) * 1, int(rng.integers(1, 400)), int(rng.integers(1, 17)), 0) for _ in range(40)]
+    cases += [(int(rng.integers(1, 2500)) * 2, int(rng.integers(1, 400)), int(rng.integers(1, 17)), 1) for _ in range(40)]
+    sched = (ctypes.c_int32 * 5)()
+    first, ln = ctypes.c_int64(), ctypes.c_int32()
+    for n_tiles, grid, chunk, merge in cases:
+        nxt, q = 0, 0
+        while True:
+            assert lib.iris_debug_claims(n_tiles, grid, chunk, merge, q, sched, ctypes.byref(first), ctypes.byref(ln)) == 0
+            if first.value >= n_tiles:
+                break
+            assert first.value == nxt, (n_tiles, grid, chunk, merge, q)
+            assert ln.value >= 1
+            if merge:
+                assert first.value % 2 == 0 and ln.value % 2 == 0
+            nxt = min(n_tiles, first.value + ln.value)
+            q += 1
+            assert q <= n_tiles + 1
+        assert nxt == n_tiles, (n_tiles, grid, chunk, merge)
+        ch, mid, tail, n_big, n_mid = list(sched)
+        assert tail <= mid <= ch
+        if n_tiles > grid * 8 and ch > (2 if merge else 1):    # a long launch ends on single tiles (tile pairs)
+            assert tail == (2 if merge else 1) and n_big > 0
