@@ -50,7 +50,7 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_fused<FM_MEL> launch of the configs[1]
     workload, read from the newest committed `ncu --set full` capture under profiles/ (below the
     algorithmic bytes: the 175 MB of banks are shared by the clips and partly stay in the 126 MB
-    L2, and the mel rows stay in L2 for k_logmel_post)."""
+    L2; measured with ncu's own cache flush in front of the launch, in place it is 559-575 MB read)."""
     import glob
     import re
     unit = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
