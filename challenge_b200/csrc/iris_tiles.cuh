@@ -46,7 +46,11 @@ __host__ __device__ inline long long claim_range(int chunk, int chunk_mid, int c
 }
 
 // tile = (clip * tiles_per_clip + time_tile) * n_pairs + pair, per_clip = tiles_per_clip * n_pairs
-__device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile, int per_clip) {
+// seg_cache / keep_cache: the clip's segments and their keep flags (1 = kept or not a voice) staged in
+// shared memory by the caller (k_labels: one round trip for the CTA instead of two dependent global
+// loads per segment and tile), or null: read them from the plan.
+__device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile, int per_clip,
+                                                 const Seg* seg_cache = nullptr, const uint8_t* keep_cache = nullptr) {
     const int FR = p.fr;
     // tile order: clip, then time, then channel pair -- the pairs of one (clip, time) range are
     // consecutive tiles (same work chunk), so the partial sectors they write to the same
@@ -59,11 +63,12 @@ __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile,
     unsigned char* blk = p.tile_blocks + size_t(tile) * p.tile_stride;
     StageDesc* d = reinterpret_cast<StageDesc*>(blk + 32);
     int n = 0;
-    const int s1 = p.seg_ptr[b + 1];
-    for (int s = p.seg_ptr[b]; s < s1; ++s) {
-        const Seg sg = p.segs[s];
+    const int s0 = p.seg_ptr[b], s1 = p.seg_ptr[b + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Seg sg = seg_cache ? seg_cache[s - s0] : p.segs[s];
         const int lo = max(sg.t_lo, t0), hi = min(sg.t_hi, t_end);
-        if (lo >= hi || (sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0)) continue;
+        const bool kept = seg_cache ? keep_cache[s - s0] != 0 : !(sg.keep_idx >= 0 && p.keep[sg.keep_idx] == 0);
+        if (lo >= hi || !kept) continue;
         if ((p.seg_select == 1 && sg.keep_idx < 0) || (p.seg_select == 2 && sg.keep_idx >= 0)) continue;
         if (n < p.max_segs) {
             StageDesc e;

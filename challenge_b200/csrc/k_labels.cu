@@ -91,7 +91,19 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int 
     for (int i = threadIdx.x; i < TK; i += blockDim.x) out[i] = L[i];
     if (build_tiles) {   // (the barrier above also orders thread 0's keep flags before these reads)
         const int per_clip = ((fp.T + fp.fr - 1) / fp.fr) * fp.n_pairs;
-        for (int r = threadIdx.x; r < per_clip; r += blockDim.x) build_tile_block(fp, b * per_clip + r, per_clip);
+        // the clip's segments + keep flags once into shared memory, then one thread per tile
+        __shared__ Seg s_segs[kMaxStages + 8];
+        __shared__ uint8_t s_kept[kMaxStages + 8];
+        const int s0 = fp.seg_ptr[b], n_seg = fp.seg_ptr[b + 1] - s0;
+        const bool cached = n_seg <= kMaxStages + 8;
+        if (cached && int(threadIdx.x) < n_seg) {
+            const Seg sg = fp.segs[s0 + threadIdx.x];
+            s_segs[threadIdx.x] = sg;
+            s_kept[threadIdx.x] = (sg.keep_idx >= 0 && fp.keep[sg.keep_idx] == 0) ? 0 : 1;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < per_clip; r += blockDim.x)
+            build_tile_block(fp, b * per_clip + r, per_clip, cached ? s_segs : nullptr, cached ? s_kept : nullptr);
     }
 }
 
