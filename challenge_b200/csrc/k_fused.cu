@@ -336,18 +336,6 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
     };
     // own_runs: the caller is the post warp (it also publishes the runs of its CTA while it waits and works)
     auto post_loop = [&](const bool own_runs) {
-#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 3   // timing experiment: the post warps only publish runs, k_logmel_post is missing
-        if (own_runs) {
-            if (lane == 0) {
-                while (*reinterpret_cast<volatile uint32_t*>(&s_exit) != uint32_t(FR)) {
-                    service_runs();
-                    __nanosleep(64);
-                }
-                service_runs();
-            }
-        }
-        return;
-#endif
         // items = (clip, part) in clip order; a clip is whole when clip_done reaches its tile count
         const uint32_t tpc = uint32_t((p.T + FR - 1) / FR) * uint32_t(p.n_pairs);
         const size_t clip_elems = size_t(p.n_mel) * p.T * C;
@@ -384,22 +372,11 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
             float4* v = reinterpret_cast<float4*>(p.out + size_t(b) * clip_elems);
             const uint32_t lo = uint32_t((uint64_t(n4) * part) / kPostParts);
             const uint32_t hi = uint32_t((uint64_t(n4) * (part + 1)) / kPostParts);
-#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 1   // timing experiment: synchronisation only
-            if (false)
-#endif
             for (uint32_t i0 = lo + lane; i0 < hi; i0 += 32 * kPostUnroll) {
                 float4 a[kPostUnroll];
 #pragma unroll
                 for (int u = 0; u < kPostUnroll; ++u)
                     if (i0 + 32 * u < hi) a[u] = __ldcg(v + i0 + 32 * u);
-#if defined(IRIS_POST_EXP) && IRIS_POST_EXP == 2   // timing experiment: loads only
-                float acc = 0.f;
-#pragma unroll
-                for (int u = 0; u < kPostUnroll; ++u)
-                    if (i0 + 32 * u < hi) acc += a[u].x + a[u].y + a[u].z + a[u].w;
-                if (acc == 1.2345e-30f) v[i0] = a[0];
-                continue;
-#endif
 #pragma unroll
                 for (int u = 0; u < kPostUnroll; ++u)
                     if (i0 + 32 * u < hi) {
@@ -629,11 +606,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
         const uint64_t pol_keep = l2_policy_evict_last();
         // mel rows are re-read by k_logmel_post: ask L2 to keep them (fixed variants: hints are on; a
         // 256-clip batch does not fit anyway, but the hint measures 4-8 us better than plain stores)
-#ifdef IRIS_EXP_NOHINT
-        const bool keep_l2 = false;
-#else
         const bool keep_l2 = kFix ? bool(EPI & EPI_MINMAX) : (kMel && p.l2_hints && do_minmax);
-#endif
         float* clip_out = p.out;      // out[b, 0, 0, 0] of the current clip (mel modes)
         uint32_t zbits = 0;
         int zb_clip = -1;
@@ -875,11 +848,7 @@ __global__ void __maxnreg__(IRIS_MAX_REGS) k_fused(const __grid_constant__ Fused
                         if (mrow != 0xffffu) {
                             float* o = o_t + mrow * row_elems;
                             float a0 = acc0[r], a1 = acc1[r];
-#ifdef IRIS_EXP_NOMM
-                            if (false) {
-#else
                             if (do_minmax) {
-#endif
                                 mn = fminf(mn, has1 ? fminf(a0, a1) : a0);
                                 mx = fmaxf(mx, has1 ? fmaxf(a0, a1) : a0);
                             }
