@@ -46,11 +46,12 @@ __host__ __device__ inline long long claim_range(int chunk, int chunk_mid, int c
 }
 
 // tile = (clip * tiles_per_clip + time_tile) * n_pairs + pair, per_clip = tiles_per_clip * n_pairs
-// seg_cache / keep_cache: the clip's segments and their keep flags (1 = kept or not a voice) staged in
-// shared memory by the caller (k_labels: one round trip for the CTA instead of two dependent global
-// loads per segment and tile), or null: read them from the plan.
+// seg_cache / keep_cache / tm_cache / fm_cache: the clip's segments, their keep flags (1 = kept or not a
+// voice) and its mask rectangles staged in shared memory by the caller (k_labels), or null: read them
+// from the plan.
 __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile, int per_clip,
-                                                 const Seg* seg_cache = nullptr, const uint8_t* keep_cache = nullptr) {
+                                                 const Seg* seg_cache = nullptr, const uint8_t* keep_cache = nullptr,
+                                                 const int32_t* tm_cache = nullptr, const int32_t* fm_cache = nullptr) {
     const int FR = p.fr;
     // tile order: clip, then time, then channel pair -- the pairs of one (clip, time) range are
     // consecutive tiles (same work chunk), so the partial sectors they write to the same
@@ -86,7 +87,7 @@ __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile,
     }
     uint32_t tbits = 0;
     if (p.tmask != nullptr) {
-        const int32_t* tm = p.tmask + size_t(b) * p.n_tmask * 2;
+        const int32_t* tm = tm_cache ? tm_cache : p.tmask + size_t(b) * p.n_tmask * 2;
         for (int i = 0; i < p.n_tmask; ++i) {
             const int size = tm[2 * i], off = tm[2 * i + 1];
             const int lo = max(off, t0), hi = min(off + size, t_end);
@@ -104,7 +105,7 @@ __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile,
             for (int f = max(off, 0); f < min(off + size, 128); ++f) w[f >> 5] |= 1u << (f & 31);
         };
         if (p.fmask != nullptr) {
-            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
+            const int32_t* fk = fm_cache ? fm_cache : p.fmask + size_t(b) * p.n_fmask * 2;
             for (int i = 0; i < p.n_fmask; ++i) zero_bins(fk[2 * i + 1], fk[2 * i]);
         }
         if (p.filter_k > 0) zero_bins(1, p.filter_k);
@@ -114,7 +115,7 @@ __device__ __forceinline__ void build_tile_block(const FusedParams& p, int tile,
 #pragma unroll
         for (int i = 0; i < 8; ++i) fm[i] = 0;
         if (p.fmask != nullptr) {
-            const int32_t* fk = p.fmask + size_t(b) * p.n_fmask * 2;
+            const int32_t* fk = fm_cache ? fm_cache : p.fmask + size_t(b) * p.n_fmask * 2;
             for (int i = 0; i < p.n_fmask && i < 4; ++i) {
                 fm[2 * i] = int16_t(fk[2 * i]);
                 fm[2 * i + 1] = int16_t(fk[2 * i + 1]);

@@ -35,6 +35,18 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int 
     // ONE flattened gather of all V x T activity bytes: the loads are independent, so they
     // pipeline instead of paying a memory round trip per voice
     __shared__ int s_id[64], s_shift[64], s_kT[64];
+    // tile lists (build_tiles): the clip's segment range rides on the metadata round trip, its segments
+    // and mask rectangles on the activity gather, the keep flags stay in shared memory -- the tile
+    // threads at the end touch no global memory but their own blocks
+    __shared__ int s_seg0, s_nseg;
+    __shared__ Seg s_segs[kMaxStages + 8];
+    __shared__ uint8_t s_kept[kMaxStages + 8];
+    __shared__ uint8_t s_keepv[64];
+    __shared__ int32_t s_tm[32], s_fm[32];
+    if (build_tiles && threadIdx.x == 32) {
+        s_seg0 = fp.seg_ptr[b];
+        s_nseg = fp.seg_ptr[b + 1] - s_seg0;
+    }
     for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
         // one round trip: the frame count of the voice comes with the plan (0 behind n_voices)
         s_id[v] = p.voice_id[size_t(b) * p.V + v];
@@ -57,12 +69,19 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int 
         const int v = i / p.K;
         lab[i] = v < nv ? p.bank_labels[size_t(s_id[v]) * p.K + (i - v * p.K)] : 0.f;
     }
+    const bool seg_cached = build_tiles && s_nseg <= kMaxStages + 8 && fp.n_tmask <= 16 && fp.n_fmask <= 16;
+    if (seg_cached) {
+        const int t = int(blockDim.x) - 1 - int(threadIdx.x);   // the last threads: the first ones carry the gather's tail
+        if (t < s_nseg) s_segs[t] = fp.segs[s_seg0 + t];
+        if (fp.tmask && t < 2 * fp.n_tmask) s_tm[t] = fp.tmask[size_t(b) * fp.n_tmask * 2 + t];
+        if (fp.fmask && t < 2 * fp.n_fmask) s_fm[t] = fp.fmask[size_t(b) * fp.n_fmask * 2 + t];
+    }
     __syncthreads();
     for (int v = 0; v < p.V; ++v) {
         float* lv = p.labels_vtk ? p.labels_vtk + (size_t(b) * p.V + v) * TK : nullptr;
         if (v >= nv) {   // uniform
             if (lv) for (int i = threadIdx.x; i < TK; i += blockDim.x) lv[i] = 0.f;
-            if (threadIdx.x == 0) p.keep[size_t(b) * p.V + v] = 0;
+            if (threadIdx.x == 0) { p.keep[size_t(b) * p.V + v] = 0; s_keepv[v] = 0; }
             continue;
         }
         const uint8_t* av = act + v * p.T;
@@ -76,7 +95,7 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int 
             for (int c = 0; c < p.K; ++c) hit |= (L[t * p.K + c] + lb[c] * a >= 2.f);
         }
         const int keep_i = __syncthreads_or(hit) ? 0 : 1;
-        if (threadIdx.x == 0) p.keep[size_t(b) * p.V + v] = uint8_t(keep_i);
+        if (threadIdx.x == 0) { p.keep[size_t(b) * p.V + v] = uint8_t(keep_i); s_keepv[v] = uint8_t(keep_i); }
         const float keep = keep_i ? 1.f : 0.f;
         for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
             const float a = av[t] ? 1.f : 0.f;
@@ -92,19 +111,17 @@ __global__ void __launch_bounds__(1024) k_labels(const LabelParams p, const int 
     for (int i = threadIdx.x; i < TK; i += blockDim.x) out[i] = L[i];
     if (build_tiles) {   // (the barrier above also orders thread 0's keep flags before these reads)
         const int per_clip = ((fp.T + fp.fr - 1) / fp.fr) * fp.n_pairs;
-        // the clip's segments + keep flags once into shared memory, then one thread per tile
-        __shared__ Seg s_segs[kMaxStages + 8];
-        __shared__ uint8_t s_kept[kMaxStages + 8];
-        const int s0 = fp.seg_ptr[b], n_seg = fp.seg_ptr[b + 1] - s0;
-        const bool cached = n_seg <= kMaxStages + 8;
-        if (cached && int(threadIdx.x) < n_seg) {
-            const Seg sg = fp.segs[s0 + threadIdx.x];
-            s_segs[threadIdx.x] = sg;
-            s_kept[threadIdx.x] = (sg.keep_idx >= 0 && fp.keep[sg.keep_idx] == 0) ? 0 : 1;
+        if (seg_cached) {
+            // keep_idx of a voice segment is b * V + v (iris_plan_upload): its flag is in shared memory
+            if (int(threadIdx.x) < s_nseg) {
+                const int ki = s_segs[threadIdx.x].keep_idx;
+                s_kept[threadIdx.x] = ki < 0 ? 1 : s_keepv[ki - b * p.V];
+            }
+            __syncthreads();
         }
-        __syncthreads();
         for (int r = threadIdx.x; r < per_clip; r += blockDim.x)
-            build_tile_block(fp, b * per_clip + r, per_clip, cached ? s_segs : nullptr, cached ? s_kept : nullptr);
+            build_tile_block(fp, b * per_clip + r, per_clip, seg_cached ? s_segs : nullptr, seg_cached ? s_kept : nullptr,
+                             seg_cached ? s_tm : nullptr, seg_cached ? s_fm : nullptr);
     }
 }
 
